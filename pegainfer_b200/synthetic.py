@@ -1,0 +1,65 @@
+"""Random-init Qwen3 checkpoints and synthetic prompts (no network, no real weights).
+
+Weights follow HF ``Qwen3ForCausalLM`` default init (Linear / Embedding N(0, 0.02),
+norm weights 1.0 -- SURVEY.md section 8d) under the HF tensor names the reference's
+loader reads (pegainfer-qwen3-4b/src/weights.rs:100-291).  Prompt ids follow
+pegainfer-server/src/bin/bench_serving.rs:761-763: ``(i % 1000) + 100``.
+"""
+from __future__ import annotations
+
+import torch
+
+from .config import Qwen3Config
+
+
+def synthetic_prompt(n: int, offset: int = 0) -> list[int]:
+    return [((i + offset) % 1000) + 100 for i in range(n)]
+
+
+def weight_shapes(cfg: Qwen3Config) -> dict[str, tuple[int, ...]]:
+    c = cfg
+    s: dict[str, tuple[int, ...]] = {"model.embed_tokens.weight": (c.vocab_size, c.hidden_size)}
+    for i in range(c.num_hidden_layers):
+        p = f"model.layers.{i}."
+        s[p + "input_layernorm.weight"] = (c.hidden_size,)
+        s[p + "self_attn.q_proj.weight"] = (c.q_dim, c.hidden_size)
+        s[p + "self_attn.k_proj.weight"] = (c.kv_dim, c.hidden_size)
+        s[p + "self_attn.v_proj.weight"] = (c.kv_dim, c.hidden_size)
+        s[p + "self_attn.o_proj.weight"] = (c.hidden_size, c.q_dim)
+        s[p + "self_attn.q_norm.weight"] = (c.head_dim,)
+        s[p + "self_attn.k_norm.weight"] = (c.head_dim,)
+        s[p + "post_attention_layernorm.weight"] = (c.hidden_size,)
+        s[p + "mlp.gate_proj.weight"] = (c.intermediate_size, c.hidden_size)
+        s[p + "mlp.up_proj.weight"] = (c.intermediate_size, c.hidden_size)
+        s[p + "mlp.down_proj.weight"] = (c.hidden_size, c.intermediate_size)
+    s["model.norm.weight"] = (c.hidden_size,)
+    if not c.tie_word_embeddings:
+        s["lm_head.weight"] = (c.vocab_size, c.hidden_size)
+    return s
+
+
+def random_weights(cfg: Qwen3Config, seed: int = 0, device: str = "cpu",
+                   norm_jitter: float = 0.0) -> dict[str, torch.Tensor]:
+    """bf16 tensors by HF name.  Deterministic per (seed, device type, tensor order).
+
+    ``norm_jitter`` > 0 perturbs norm weights away from 1.0 (tests only) so a
+    dropped weight multiply cannot hide.
+    """
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out: dict[str, torch.Tensor] = {}
+    for name, shape in weight_shapes(cfg).items():
+        if len(shape) == 1:
+            t = torch.ones(shape, dtype=torch.float32, device=device)
+            if norm_jitter:
+                t += norm_jitter * torch.randn(shape, generator=g, dtype=torch.float32, device=device)
+        else:
+            t = torch.randn(shape, generator=g, dtype=torch.float32, device=device) * 0.02
+        out[name] = t.to(torch.bfloat16)
+    return out
+
+
+def to_numpy_bits(weights: dict[str, torch.Tensor]):
+    """bf16 torch tensors -> numpy uint16 bit patterns (what the CPU oracle eats)."""
+    return {k: v.detach().cpu().contiguous().view(torch.int16).numpy().view("uint16")
+            for k, v in weights.items()}
