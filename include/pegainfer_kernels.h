@@ -1,0 +1,247 @@
+/*
+ * pegainfer_kernels.h -- C ABI of libpegainfer_kernels_b200.so
+ *
+ * Drop-in boundary for the Qwen3 forward-pass hot path of xiaguan/pegainfer:
+ * every entry point below has the NAME, ARGUMENT ORDER and ERROR CONVENTION of
+ * the `unsafe extern "C"` declaration in the reference's
+ * pegainfer-kernels/src/ffi.rs that it replaces (file:line cited per symbol), so
+ * the reference's Rust `ops::*` wrappers bind to this library unchanged
+ * (INTEGRATION.md shows the build.rs change).  Section "B200 extensions" adds the
+ * fused / tensor-parallel entry points the reference does not have.
+ *
+ * Conventions (reference: SURVEY.md 8b):
+ *  - pk_bf16 = uint16_t bf16 bit pattern (`pub type Half = u16`, ffi.rs:4).
+ *  - All pointers are DEVICE pointers unless a comment says host.
+ *  - Activations are `HiddenStates[dim, tokens]`: token t occupies elements
+ *    [t*dim, (t+1)*dim) (pegainfer-kernels/src/tensor.rs:210-217); weights are
+ *    row-major [out, in] (tensor.rs:136-141).
+ *  - Buffers are owned by the caller.  The library owns only per-thread scratch
+ *    created by cublas_init() and never allocates inside a launch, so every
+ *    launch entry point is CUDA-graph-capture safe.
+ *  - Error styles kept from the reference: `void` (errors surface at the next
+ *    sync), `pk_curesult` (= cudaGetLastError cast), `int` (cudaError, 0 = ok,
+ *    -1 = invalid argument).
+ *  - There is NO CPU fallback: without a CUDA device every launch fails.
+ */
+#ifndef PEGAINFER_KERNELS_H_
+#define PEGAINFER_KERNELS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t pk_bf16;
+typedef struct CUstream_st* pk_stream; /* CUstream == cudaStream_t */
+typedef int pk_curesult;               /* CUresult */
+
+/* ---- context / handles: ffi.rs:159-161, csrc/linear.cu:14-42 ----------------
+ * Call cuda_set_device + cublas_init once per rank thread.  cublas_init keeps its
+ * historical name; here it creates the per-thread split-KV / top-1 scratch (the
+ * reference allocates its 32 MB cuBLAS workspace at the same point). */
+int  cuda_set_device(int device_ordinal);
+void cublas_init(void);
+void cublas_destroy(void);
+
+/* ---- embedding: ffi.rs:78-96,143-149; csrc/elementwise.cu:49-112 ------------ */
+pk_curesult embedding_batched_cuda(const pk_bf16* embed, const uint32_t* token_ids, pk_bf16* out,
+                                   int hidden_size, int seq_len, pk_stream stream);
+pk_curesult embedding_decode_cuda(const pk_bf16* embed, const uint32_t* token_id, pk_bf16* out,
+                                  int hidden_size, pk_stream stream);
+pk_curesult embedding_batched_vocab_shard_cuda(const pk_bf16* embed, const uint32_t* token_ids,
+                                               pk_bf16* out, int hidden_size, int seq_len,
+                                               uint32_t vocab_start, uint32_t part_vocab_size,
+                                               pk_stream stream);
+
+/* ---- norms: ffi.rs:22-68; csrc/flashinfer_norm.cu:49-105 --------------------
+ * fused_add_rms_norm: hidden += residual (bf16-rounded store); out = RMSNorm of the
+ * UNROUNDED fp32 sum.  No staging memcpy (the reference does one). */
+void rms_norm_cuda(const pk_bf16* x, const pk_bf16* weight, pk_bf16* out, int n, float eps,
+                   pk_stream stream);
+void rms_norm_batched_cuda(const pk_bf16* x, const pk_bf16* weight, pk_bf16* out, int hidden_dim,
+                           int seq_len, float eps, pk_stream stream);
+void fused_add_rms_norm_cuda(pk_bf16* hidden, const pk_bf16* residual, const pk_bf16* weight,
+                             pk_bf16* out, int n, float eps, pk_stream stream);
+void fused_add_rms_norm_batched_cuda(pk_bf16* hidden, const pk_bf16* residual,
+                                     const pk_bf16* weight, pk_bf16* out, int hidden_dim,
+                                     int batch_size, float eps, pk_stream stream);
+
+/* ---- elementwise: ffi.rs:41-47,70-76,151-157 -------------------------------- */
+pk_curesult add_cuda(const pk_bf16* a, const pk_bf16* b, pk_bf16* out, int n, pk_stream stream);
+pk_curesult silu_mul_triton_aot_cuda(const pk_bf16* gate, const pk_bf16* up, pk_bf16* out, int n,
+                                     pk_stream stream); /* historical name; rounds SiLU to bf16 */
+void silu_mul_fused_cuda(const pk_bf16* gate_up, pk_bf16* out, int intermediate_size, int bs,
+                         pk_stream stream);
+
+/* ---- GEMM / GEMV: ffi.rs:122-140; csrc/linear.cu:48-78 ----------------------
+ * Y[M,N] (col-major, ld=M) = W[M,K] (row-major) * X[K,N] (col-major, ld=K);
+ * bf16 in, fp32 accumulate, one bf16 rounding.
+ * gemm_cuda: prefill (tcgen05 tensor cores).  gemm_graphsafe_cuda: decode; N<=4 runs
+ * the HBM-streaming GEMV, larger N the same tensor-core path.  Both are capture safe. */
+void gemm_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
+               pk_stream stream);
+void gemm_graphsafe_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
+                         pk_stream stream);
+
+/* ---- QK-norm + RoPE: ffi.rs:164-178,1143-1157; csrc/prefill_attention.cu:12-159
+ * In place on q [nq*hd, T] and k [nkv*hd, T]; head_dim must be 128 (as the reference). */
+void prefill_qk_norm_rope_only_cuda(pk_bf16* q_batch, pk_bf16* k_batch,
+                                    const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight,
+                                    const pk_bf16* cos_cache, const pk_bf16* sin_cache,
+                                    int num_q_heads, int num_kv_heads, int head_dim, int seq_len,
+                                    int start_pos, float rms_eps, pk_stream stream);
+void qk_norm_rope_batched_decode_cuda(pk_bf16* q, pk_bf16* k, const pk_bf16* q_norm_weight,
+                                      const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+                                      const pk_bf16* sin_cache, const int* positions,
+                                      int num_q_heads, int num_kv_heads, int head_dim,
+                                      int batch_size, float rms_eps, pk_stream stream);
+
+/* ---- paged KV + attention: ffi.rs:1160-1283,1337-1385; csrc/paged_attention.cu */
+int paged_kv_scatter_cuda(const pk_bf16* kv_data, int64_t k_offset_elems, int64_t v_offset_elems,
+                          const int* page_indices, const int* page_indptr,
+                          const int* last_page_len_d, const pk_bf16* src_k, const pk_bf16* src_v,
+                          const int* batch_indices, const int* positions, int nnz,
+                          int num_kv_heads, int head_dim, int page_size, int64_t stride_page,
+                          int64_t src_stride_n, int64_t src_stride_h, pk_stream stream);
+
+/* host-only planning helpers (csrc/paged_attention.cu:343-397) */
+int batch_prefill_paged_num_tiles(int seq_len, int num_qo_heads, int num_kv_heads, int head_dim);
+int batch_prefill_paged_num_tiles_with_cta_tile_q(int seq_len, int num_qo_heads, int num_kv_heads,
+                                                  int head_dim, int cta_tile_q_override);
+int batch_prefill_cta_tile_q(int total_seq_len, int num_qo_heads, int num_kv_heads, int head_dim);
+int batch_prefill_cta_tile_q_with_override(int total_seq_len, int num_qo_heads, int num_kv_heads,
+                                           int head_dim, int cta_tile_q_override);
+
+int batch_prefill_paged_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data,
+                             int64_t k_offset_elems, int64_t v_offset_elems,
+                             const int* page_indices, const int* page_indptr,
+                             const int* last_page_len_d, const int* q_indptr,
+                             const int* request_indices, const int* qo_tile_indices,
+                             const int* kv_tile_indices, const int* kv_chunk_size_ptr,
+                             const uint32_t* total_num_rows, int num_qo_heads, int num_kv_heads,
+                             int head_dim, int page_size, int seq_len, int batch_size,
+                             int padded_batch_size, int64_t stride_page, float sm_scale,
+                             pk_stream stream);
+int batch_prefill_paged_cuda_with_cta_tile_q(
+    const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
+    int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
+    const int* last_page_len_d, const int* q_indptr, const int* request_indices,
+    const int* qo_tile_indices, const int* kv_tile_indices, const int* kv_chunk_size_ptr,
+    const uint32_t* total_num_rows, int num_qo_heads, int num_kv_heads, int head_dim,
+    int page_size, int seq_len, int batch_size, int padded_batch_size, int64_t stride_page,
+    float sm_scale, int cta_tile_q_override, pk_stream stream);
+int single_prefill_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16* k_cache,
+                        const pk_bf16* v_cache, int num_qo_heads, int num_kv_heads, int head_dim,
+                        int seq_len, int kv_len, int max_seq_len, float sm_scale,
+                        pk_stream stream);
+
+int paged_attention_decode_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data,
+                                int64_t k_offset_elems, int64_t v_offset_elems,
+                                const int* page_indices, const int* page_indptr,
+                                const int* last_page_len_d, const int* request_indices,
+                                const int* kv_tile_indices, const int* kv_chunk_size_ptr,
+                                int num_qo_heads, int num_kv_heads, int head_dim, int page_size,
+                                int batch_size, int64_t stride_page, float sm_scale,
+                                pk_stream stream);
+int paged_attention_decode_split_kv_cuda(
+    const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
+    int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
+    const int* last_page_len_d, const int* request_indices, const int* kv_tile_indices,
+    const int* kv_chunk_size_ptr, const int* o_indptr, const uint8_t* block_valid_mask,
+    pk_bf16* tmp_v, float* tmp_s, int num_qo_heads, int num_kv_heads, int head_dim, int page_size,
+    int batch_size, int padded_batch_size, int64_t stride_page, float sm_scale, pk_stream stream);
+
+/* ---- sampling: ffi.rs:98-108; csrc/argmax.cu, csrc/flashinfer_top1.cu --------
+ * Both pick the LOWEST index among equal maxima (the reference's radix top-1 leaves
+ * tie order undefined).  row_states_scratch: >= 4 KiB (the reference passes 1 MiB). */
+void argmax_cuda(const pk_bf16* x, int* out, int n, pk_stream stream);
+void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
+                          uint8_t* row_states_scratch, int* output, int vocab_size,
+                          pk_stream stream);
+
+/* =============================== B200 extensions ===============================
+ * Not in ffi.rs.  The fused decode layer used by the host mirror
+ * (pegainfer_b200/csrc/host) and the TP hook north_star asks pegainfer-comm to gain. */
+
+/* Library / build identification ("pegainfer-kernels-b200 sm_100a ..."). */
+const char* pk_b200_version(void);
+/* Number of kernels launched by this library on the calling thread since the last
+ * reset (bench.py's gpu_launches; counts launches recorded into a capture too). */
+int64_t pk_b200_launch_count(int reset);
+/* Enable (1) / disable (0) programmatic dependent launch on this thread's launches. */
+void pk_b200_set_pdl(int enable);
+
+/* GEMV with fused prologue/epilogue for decode (N == 1..4 tokens), one launch:
+ *   x_mode 0: x = X as is ([N, K]).
+ *   x_mode 1: X is `hidden` [N, K]; x = RMSNorm(hidden + residual) * norm_w computed in the
+ *             prologue exactly as fused_add_rms_norm_batched_cuda would (unrounded fp32 sum,
+ *             one rounding); CTA 0 also stores bf16(hidden + residual) to hidden_out (must NOT
+ *             alias X: other CTAs still read it) and x to normed_out (optional).
+ *   epi 0:    Y = bf16(W x); rows are routed to up to three outputs: rows [0, seg_rows[0]) ->
+ *             Y[0], the next seg_rows[1] -> Y[1], the rest -> Y[2] (the fused q|k|v projection).
+ *   epi 1:    SwiGLU: W = [M gate rows | M up rows];
+ *             Y[0][m] = bf16(silu(bf16(gate_m.x)) * bf16(up_m.x))  (csrc/fused_proj.cu:44-63). */
+typedef struct {
+  const pk_bf16* W;
+  const pk_bf16* X;
+  pk_bf16* Y[3];
+  int seg_rows[3];
+  int M, N, K;
+  int x_mode;
+  const pk_bf16* residual;
+  const pk_bf16* norm_w;
+  float eps;
+  pk_bf16* hidden_out;
+  pk_bf16* normed_out;
+  int epi;
+} pk_b200_gemv_args;
+int pk_b200_gemv_fused(const pk_b200_gemv_args* args, pk_stream stream);
+
+/* QK-norm + RoPE + KV append + split-KV GQA decode attention + merge in ONE launch.
+ * q/k/v are the raw projections of the step ([dim, bs]); k is normed/roped and both k, v
+ * are appended at `positions` before use.  partial_* : fp32 scratch
+ * [bs * max_chunks * nq * (hd + 2)], counters: int[bs * nkv] zero-initialised (self-resetting). */
+int pk_b200_decode_attention_fused(
+    const pk_bf16* q, const pk_bf16* k, const pk_bf16* v, pk_bf16* output, pk_bf16* kv_data,
+    int64_t k_offset_elems, int64_t v_offset_elems, const int* page_indices,
+    const int* page_indptr, const int* last_page_len_d, const int* positions,
+    const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+    const pk_bf16* sin_cache, float rms_eps, float* partial_scratch, int* counters,
+    int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
+    int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream);
+
+/* ---- TP all-reduce hook (pegainfer-qwen3-4b/src/weights.rs:396-405) ----------
+ * One-shot all-reduce over NVLink peer memory: every rank owns a symmetric staging
+ * buffer; peers' buffers are mapped (cudaIpc / peer access).  In-place SUM over
+ * [H, T] bf16 on the rank's stream, graph-capturable.
+ *   pk_tp_comm: opaque; created from the world's staging + flag pointers as mapped in
+ *   THIS process (index = rank). */
+typedef struct pk_tp_comm pk_tp_comm;
+/* Bytes of the per-rank flag array (zero-initialised device memory). */
+int64_t pk_tp_flag_bytes(void);
+/* staging_ptrs[p] / flag_ptrs[p]: rank p's staging / flag buffers as mapped in THIS process
+ * (own buffers for p == rank, cudaIpc-opened for peers).  staging_bytes: size of each staging
+ * buffer; it is cut into 2 slots x world source regions. */
+pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
+                              void* const* flag_ptrs, int64_t staging_bytes);
+void pk_tp_comm_destroy(pk_tp_comm* comm);
+/* Largest row count one call can reduce for rows of hidden_dim bf16 (callers chunk above it). */
+int64_t pk_tp_max_rows(pk_tp_comm* comm, int hidden_dim);
+/* all_reduce_hidden(&mut HiddenStates): in-place SUM (fp32 in rank order, one bf16 rounding). */
+int pk_tp_all_reduce(pk_tp_comm* comm, pk_bf16* hidden, int64_t n, pk_stream stream);
+int pk_tp_all_reduce_rows(pk_tp_comm* comm, pk_bf16* hidden, int hidden_dim, int rows,
+                          pk_stream stream);
+/* all-reduce(partial) fused with `hidden += sum; out = RMSNorm(hidden) * weight`. */
+int pk_tp_all_reduce_add_rms_norm(pk_tp_comm* comm, pk_bf16* hidden, const pk_bf16* partial,
+                                  const pk_bf16* weight, pk_bf16* out, int hidden_dim,
+                                  int batch_size, float eps, pk_stream stream);
+/* cudaIpc plumbing for one-process-per-GPU peers (64-byte handles travel over torch.distributed) */
+int pk_tp_ipc_export(void* dev_ptr, void* handle_out_64);
+int pk_tp_ipc_open(const void* handle_64, void** dev_ptr_out);
+int pk_tp_ipc_close(void* dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEGAINFER_KERNELS_H_ */

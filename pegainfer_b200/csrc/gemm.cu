@@ -1,0 +1,360 @@
+// Prefill GEMM: Y[M, N] = W[M, K] x X[K, N] on the 5th-generation tensor cores.
+// Replaces `gemm_cuda` (csrc/linear.cu:48-62, a cublasGemmEx call in the reference).
+// bf16 x bf16 -> fp32 accumulate (TMEM) -> one bf16 rounding, as CUBLAS_COMPUTE_32F.
+//
+// Mapping (both operands are K-major in memory, so no transposes anywhere):
+//   A = X  : [tokens, K]   -> UMMA M dimension = 128 tokens  (TMEM lane  = token)
+//   B = W  : [features, K] -> UMMA N dimension = BN features (TMEM column = feature)
+//   D[token, feature] lands so that one thread owns one token row: the epilogue converts 32
+//   consecutive features to bf16 and stores 64 contiguous bytes of HiddenStates[features, tokens].
+// Pipeline (warp-specialised, persistent, one CTA per SM):
+//   warp 0  : TMA producer   -- cp.async.bulk.tensor 2-D tiles, 128-B swizzle, mbarrier tx
+//   warp 1  : MMA issuer     -- one elected lane issues tcgen05.mma (M128 x BN x K16), commits
+//                               free the smem stage / publish the TMEM accumulator
+//   warps 2-5: epilogue      -- tcgen05.ld 32x32b.x32 -> bf16 -> global; double-buffered TMEM
+//                               accumulators so the epilogue of tile i overlaps the MMAs of i+1
+// Tensor-bound: 2*M*N*K flops per call; roofline against MEASURED_PEAKS.json bf16_tflops.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pk {
+
+// ------------------------------------------------------------------ SIMT fallback
+// Shapes TMA cannot take (K % 8 != 0, unaligned bases) and the PK_GEMM_IMPL=simt debug switch.
+__global__ void gemm_simt_kernel(const bf16* __restrict__ W, const bf16* __restrict__ X,
+                                 bf16* __restrict__ Y, int M, int N, int K) {
+  constexpr int T = 64, KT = 32;
+  __shared__ float ws[KT][T + 1], xs[KT][T + 1];
+  pdl_wait();
+  const int m0 = blockIdx.x * T, n0 = blockIdx.y * T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    for (int i = threadIdx.x; i < T * KT; i += 256) {
+      const int r = i / KT, c = i % KT;
+      ws[c][r] = (m0 + r < M && k0 + c < K) ? bf2f(W[(size_t)(m0 + r) * K + k0 + c]) : 0.f;
+      xs[c][r] = (n0 + r < N && k0 + c < K) ? bf2f(X[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < KT; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = ws[k][tx * 4 + i];
+        b[i] = xs[k][ty * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(a[i], b[j], acc[j][i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + tx * 4 + i, n = n0 + ty * 4 + j;
+      if (m < M && n < N) Y[(size_t)n * M + m] = f2bf(acc[j][i]);
+    }
+}
+
+// ------------------------------------------------------------------ tcgen05 path
+constexpr int BM = 128;  // tokens per tile (UMMA M)
+constexpr int BK = 64;   // K elements per stage = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 format):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x
+// 128 B = 1024) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               bf16* __restrict__ Y, int M /*features*/, int N /*tokens*/, int K) {
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (N + BM - 1) / BM, n_tiles = (M + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mb = tile % m_tiles, nb = tile / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty + s, (uint32_t)(((it / STAGES) & 1) ^ 1));
+          mbar_expect_tx(full + s, STAGE_BYTES);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          tma_load_2d(st, &map_x, kb * BK, mb * BM, full + s);
+          tma_load_2d(st + A_BYTES, &map_w, kb * BK, nb * BN, full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int as = lt & 1;
+      mbar_wait(tempty + as, (uint32_t)(((lt >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance the start address by k*32 bytes inside the 128-byte swizzle span
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + s);                       // smem stage free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull + as);  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const bool vec_ok = (M % 8 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int mb = tile % m_tiles, nb = tile / m_tiles;
+      const int as = lt & 1;
+      mbar_wait(tfull + as, (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      const int tok = mb * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c, v);
+        const int f0 = nb * BN + c;
+        if (tok < N && f0 < M) {
+          bf16* dst = Y + (size_t)tok * M + f0;
+          if (vec_ok && f0 + 32 <= M) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+              o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+              o.z = pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+              o.w = pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && f0 + j < M; ++j) dst[j] = f2bf(__uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows x K bf16 row-major matrix, box = [box_rows, 64], 128-byte swizzle, OOB reads as zero
+static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16* Y, int M, int N,
+                             int K, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  auto kern = gemm_tc_kernel<BN, STAGES>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  return launch(kern, dim3(grid), dim3(kGemmThreads), smem, stream, true, mx, mw, Y, M, N, K);
+}
+
+static int gemm_impl_mode() {  // 0 tcgen05 (default), 1 simt
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PK_GEMM_IMPL");
+    mode = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return mode;
+}
+
+void launch_gemm(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  const bool tma_ok = K % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  if (tma_ok && gemm_impl_mode() == 0) {
+    const int m_tiles = (N + BM - 1) / BM;
+    const bool small = m_tiles * ((M + 255) / 256) < sm_count();
+    const int bn = small ? 128 : 256;
+    CUtensorMap mx, mw;
+    if (make_map(&mx, X, N, K, BM) && make_map(&mw, W, M, K, bn)) {
+      if (small)
+        launch_tc<128, 6>(mx, mw, Y, M, N, K, stream);
+      else
+        launch_tc<256, 4>(mx, mw, Y, M, N, K, stream);
+      return;
+    }
+  }
+  launch(gemm_simt_kernel, dim3((M + 63) / 64, (N + 63) / 64), dim3(256), 0, stream, true, W, X, Y,
+         M, N, K);
+}
+
+// defined in gemv.cu
+struct GemvArgs;
+bool gemv_stream_supported(const void* W, const void* X, int N, int K);
+void launch_gemv_generic(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K,
+                         cudaStream_t stream);
+
+}  // namespace pk
+
+extern "C" void gemm_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
+                          pk_stream stream) {
+  pk::launch_gemm((const pk::bf16*)W, (const pk::bf16*)X, (pk::bf16*)Y, M, N, K, stream);
+}

@@ -1,0 +1,382 @@
+// Decode GEMV: Y[M, N<=4] = W[M, K] x X[K, N] -- the op that is ~90 % of decode time
+// (weights: 8.04 GB/token for Qwen3-4B).  Replaces `gemm_graphsafe_cuda` (csrc/linear.cu:65-78,
+// a cuBLAS call in the reference) and adds the fused prologue/epilogue variants the B200 host
+// mirror uses.  bf16 x bf16 -> fp32 accumulate -> one bf16 rounding, as CUBLAS_COMPUTE_32F.
+//
+// HBM-bound design (roofline: 2*M*K bytes / HBM bandwidth):
+//  * grid = #SMs (x ctas_per_sm); CTA c owns the contiguous row range [c*M/G, (c+1)*M/G) so every
+//    SM streams the same number of bytes (+-1 row).
+//  * a dedicated producer warp streams the CTA's rows through a `stages`-deep shared-memory ring
+//    with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), L2 evict-first (weights are
+//    read exactly once per token); 8 consumer warps own one row each per group and reduce with
+//    warp shuffles.  Bytes in flight per SM = stages * 16 KB, independent of register count.
+//  * PDL: weights do not depend on the previous kernel, so the producer starts streaming BEFORE
+//    griddepcontrol.wait; only the activation vector waits.  The kernel triggers its dependents
+//    at entry so the next GEMV's weight prefetch overlaps this kernel's tail.
+//  * optional prologue: x = RMSNorm(hidden + residual) * w (fused_add_rms_norm semantics, same
+//    rounding points as csrc/flashinfer_norm.cu:71-105); optional epilogue: SwiGLU
+//    (csrc/fused_proj.cu:44-63) on interleaved gate/up row groups.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace pk {
+
+constexpr int kCW = 8;            // consumer warps (rows per group)
+constexpr int kKC = 1024;         // K elements per row segment per stage (2 KB)
+constexpr int kSegBytes = kKC * 2;
+constexpr int kStageBytes = kCW * kSegBytes;  // 16 KB
+constexpr int kMaxStages = 12;
+constexpr int kConsumerThreads = kCW * 32;
+
+struct GemvArgs {
+  const bf16* W;
+  const bf16* X;  // [N, K] activations, or hidden_in when x_mode == 1
+  bf16* Y[3];
+  int seg_end[3];  // cumulative row ends of the up-to-3 output segments (seg_end[2] == M)
+  int M, K;
+  int x_mode;
+  const bf16* residual;
+  const bf16* norm_w;
+  float eps;
+  bf16* hidden_out;
+  bf16* normed_out;
+  int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows)
+  int stages;
+};
+
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+  acc = fmaf(bf16_lo(w.x), bf16_lo(x.x), acc);
+  acc = fmaf(bf16_hi(w.x), bf16_hi(x.x), acc);
+  acc = fmaf(bf16_lo(w.y), bf16_lo(x.y), acc);
+  acc = fmaf(bf16_hi(w.y), bf16_hi(x.y), acc);
+  acc = fmaf(bf16_lo(w.z), bf16_lo(x.z), acc);
+  acc = fmaf(bf16_hi(w.z), bf16_hi(x.z), acc);
+  acc = fmaf(bf16_lo(w.w), bf16_lo(x.w), acc);
+  acc = fmaf(bf16_hi(w.w), bf16_hi(x.w), acc);
+  return acc;
+}
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int NTOK>
+__global__ void __launch_bounds__(kConsumerThreads + 32, 1)
+gemv_stream_kernel(const GemvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int stages = a.stages;
+  uint8_t* ring = smem;
+  bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)stages * kStageBytes);  // [NTOK][K]
+  const size_t x_bytes = (((size_t)NTOK * a.K * 2) + 15) & ~(size_t)15;
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + x_bytes);
+  uint64_t* empty = full + kMaxStages;
+  float* red = reinterpret_cast<float*>(empty + kMaxStages);  // 64 floats: reductions / SwiGLU swap
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int M = a.M, K = a.K;
+  const int rows_per_group = a.epi == 1 ? kCW / 2 : kCW;
+  const int r0 = (int)(((int64_t)blockIdx.x * M) / G);
+  const int r1 = (int)(((int64_t)(blockIdx.x + 1) * M) / G);
+  const int groups = (r1 - r0 + rows_per_group - 1) / rows_per_group;
+  const int chunks = (K + kKC - 1) / kKC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();  // let the next kernel start prefetching its weights
+
+  if (warp == kCW) {
+    // ===== producer warp: lanes 0..7 each stream one row segment per stage =====
+    const uint64_t pol = l2_evict_first_policy();
+    int it = 0;
+    for (int g = 0; g < groups; ++g) {
+      // source row of consumer slot `lane` in this group (-1: none)
+      int src = -1;
+      if (lane < kCW) {
+        const int out_row = r0 + g * rows_per_group + (a.epi == 1 ? (lane & 3) : lane);
+        if (out_row < r1) src = a.epi == 1 ? (lane < 4 ? out_row : M + out_row) : out_row;
+      }
+      const unsigned valid = __ballot_sync(0xffffffffu, src >= 0);
+      const int nvalid = __popc(valid);
+      for (int c = 0; c < chunks; ++c, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)((it / stages) & 1);
+        const int k0 = c * kKC;
+        const uint32_t bytes = (uint32_t)(min(kKC, K - k0) * 2);
+        if (lane == 0) {
+          mbar_wait(empty + s, ph ^ 1u);
+          mbar_expect_tx(full + s, bytes * (uint32_t)nvalid);
+        }
+        __syncwarp();
+        if (src >= 0)
+          bulk_g2s(ring + (size_t)s * kStageBytes + (size_t)lane * kSegBytes,
+                   a.W + (size_t)src * K + k0, bytes, full + s, pol);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  pdl_wait();  // activations come from the previous kernel
+  {
+    const int tid = threadIdx.x;  // 0..255
+    if (a.x_mode == 0) {
+      const int nv = (NTOK * K) >> 3;
+      for (int i = tid; i < nv; i += kConsumerThreads)
+        reinterpret_cast<uint4*>(xs)[i] = reinterpret_cast<const uint4*>(a.X)[i];
+    } else {
+      // x = bf16((h + r) * rsqrt(mean((h+r)^2) + eps) * w); hidden_out = bf16(h + r)
+      const int nv = K >> 3;
+      for (int n = 0; n < NTOK; ++n) {
+        const uint4* h4 = reinterpret_cast<const uint4*>(a.X + (size_t)n * K);
+        const uint4* r4 = reinterpret_cast<const uint4*>(a.residual + (size_t)n * K);
+        float ss = 0.f;
+        for (int i = tid; i < nv; i += kConsumerThreads) {
+          const uint4 h = h4[i], r = r4[i];
+          const float v[8] = {bf16_lo(h.x) + bf16_lo(r.x), bf16_hi(h.x) + bf16_hi(r.x),
+                              bf16_lo(h.y) + bf16_lo(r.y), bf16_hi(h.y) + bf16_hi(r.y),
+                              bf16_lo(h.z) + bf16_lo(r.z), bf16_hi(h.z) + bf16_hi(r.z),
+                              bf16_lo(h.w) + bf16_lo(r.w), bf16_hi(h.w) + bf16_hi(r.w)};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        consumer_bar();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCW; ++w) tot += red[w];
+        consumer_bar();
+        const float rinv = rsqrtf(tot / (float)K + a.eps);
+        const uint4* g4 = reinterpret_cast<const uint4*>(a.norm_w);
+        for (int i = tid; i < nv; i += kConsumerThreads) {
+          const uint4 h = h4[i], r = r4[i], g = g4[i];
+          const float v[8] = {bf16_lo(h.x) + bf16_lo(r.x), bf16_hi(h.x) + bf16_hi(r.x),
+                              bf16_lo(h.y) + bf16_lo(r.y), bf16_hi(h.y) + bf16_hi(r.y),
+                              bf16_lo(h.z) + bf16_lo(r.z), bf16_hi(h.z) + bf16_hi(r.z),
+                              bf16_lo(h.w) + bf16_lo(r.w), bf16_hi(h.w) + bf16_hi(r.w)};
+          uint4 o;
+          o.x = pack_bf16(v[0] * rinv * bf16_lo(g.x), v[1] * rinv * bf16_hi(g.x));
+          o.y = pack_bf16(v[2] * rinv * bf16_lo(g.y), v[3] * rinv * bf16_hi(g.y));
+          o.z = pack_bf16(v[4] * rinv * bf16_lo(g.z), v[5] * rinv * bf16_hi(g.z));
+          o.w = pack_bf16(v[6] * rinv * bf16_lo(g.w), v[7] * rinv * bf16_hi(g.w));
+          reinterpret_cast<uint4*>(xs + (size_t)n * K)[i] = o;
+          if (blockIdx.x == 0) {
+            uint4 hs;
+            hs.x = pack_bf16(v[0], v[1]);
+            hs.y = pack_bf16(v[2], v[3]);
+            hs.z = pack_bf16(v[4], v[5]);
+            hs.w = pack_bf16(v[6], v[7]);
+            reinterpret_cast<uint4*>(a.hidden_out + (size_t)n * K)[i] = hs;
+            if (a.normed_out) reinterpret_cast<uint4*>(a.normed_out + (size_t)n * K)[i] = o;
+          }
+        }
+      }
+    }
+    consumer_bar();
+  }
+
+  int it = 0;
+  for (int g = 0; g < groups; ++g) {
+    const int out_row = r0 + g * rows_per_group + (a.epi == 1 ? (warp & 3) : warp);
+    const bool has_row = out_row < r1;
+    float acc[NTOK];
+#pragma unroll
+    for (int n = 0; n < NTOK; ++n) acc[n] = 0.f;
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)((it / stages) & 1);
+      mbar_wait(full + s, ph);
+      if (has_row) {
+        const int k0 = c * kKC;
+        const int nvec = min(kKC, K - k0) >> 3;
+        const uint4* wseg =
+            reinterpret_cast<const uint4*>(ring + (size_t)s * kStageBytes + (size_t)warp * kSegBytes);
+#pragma unroll 4
+        for (int i = lane; i < nvec; i += 32) {
+          const uint4 wv = wseg[i];
+#pragma unroll
+          for (int n = 0; n < NTOK; ++n) {
+            const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)n * K + k0)[i];
+            acc[n] = dot8(wv, xv, acc[n]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+#pragma unroll
+    for (int n = 0; n < NTOK; ++n) acc[n] = warp_sum(acc[n]);
+    if (a.epi == 0) {
+      if (has_row && lane == 0) {
+        const int seg = out_row < a.seg_end[0] ? 0 : (out_row < a.seg_end[1] ? 1 : 2);
+        const int seg_lo = seg == 0 ? 0 : a.seg_end[seg - 1];
+        const int seg_m = a.seg_end[seg] - seg_lo;
+#pragma unroll
+        for (int n = 0; n < NTOK; ++n)
+          a.Y[seg][(size_t)n * seg_m + (out_row - seg_lo)] = f2bf(acc[n]);
+      }
+    } else {
+      float* sw = red + 16 + (g & 1) * 16;  // [4 rows][NTOK] double-buffered by group parity
+      if (warp >= 4 && lane == 0) {
+#pragma unroll
+        for (int n = 0; n < NTOK; ++n) sw[(warp - 4) * NTOK + n] = acc[n];
+      }
+      consumer_bar();
+      if (warp < 4 && has_row && lane == 0) {
+#pragma unroll
+        for (int n = 0; n < NTOK; ++n) {
+          const float gt = round_bf16(acc[n]);                   // gate_up_out is bf16 in the reference
+          const float up = round_bf16(sw[warp * NTOK + n]);
+          a.Y[0][(size_t)n * M + out_row] = f2bf(gt / (1.0f + expf(-gt)) * up);
+        }
+      }
+    }
+  }
+}
+
+// Shapes the streaming kernel cannot take (K % 8 != 0, unaligned pointers, N > 4 without the
+// tensor-core path): one warp per output element row, scalar loads.  Correctness only.
+__global__ void gemv_generic_kernel(const bf16* __restrict__ W, const bf16* __restrict__ X,
+                                    bf16* __restrict__ Y, int M, int N, int K) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = warp; o < (int64_t)M * N; o += nwarps) {
+    const int m = (int)(o % M), n = (int)(o / M);
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(bf2f(W[(size_t)m * K + k]), bf2f(X[(size_t)n * K + k]), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) Y[(size_t)n * M + m] = f2bf(acc);
+  }
+}
+
+static int g_gemv_stages = 0, g_gemv_ctas_per_sm = 0;
+
+static void gemv_tuning() {
+  if (g_gemv_stages == 0) {
+    const char* s = getenv("PK_GEMV_STAGES");
+    g_gemv_stages = s ? atoi(s) : 6;
+    if (g_gemv_stages < 2) g_gemv_stages = 2;
+    if (g_gemv_stages > kMaxStages) g_gemv_stages = kMaxStages;
+    const char* c = getenv("PK_GEMV_CTAS_PER_SM");
+    g_gemv_ctas_per_sm = c ? atoi(c) : 1;
+    if (g_gemv_ctas_per_sm < 1) g_gemv_ctas_per_sm = 1;
+  }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool gemv_stream_supported(const void* W, const void* X, int N, int K) {
+  return N >= 1 && N <= 4 && K % 8 == 0 && al16(W) && al16(X) && (size_t)N * K * 2 <= 96 * 1024;
+}
+
+template <int NTOK>
+static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
+  gemv_tuning();
+  int stages = g_gemv_stages;
+  const size_t x_bytes = (((size_t)NTOK * a.K * 2) + 15) & ~(size_t)15;
+  const size_t tail = 2 * kMaxStages * sizeof(uint64_t) + 64 * sizeof(float);
+  while (stages > 2 && (size_t)stages * kStageBytes + x_bytes + tail > 200 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * kStageBytes + x_bytes + tail;
+  auto kern = gemv_stream_kernel<NTOK>;
+  static thread_local size_t configured[5] = {0, 0, 0, 0, 0};
+  if (smem > configured[NTOK]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[NTOK] = smem;
+  }
+  const int rpg = a.epi == 1 ? kCW / 2 : kCW;
+  int grid = sm_count() * g_gemv_ctas_per_sm;
+  const int max_useful = (a.M + rpg - 1) / rpg;
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+  return launch(kern, dim3(grid), dim3(kConsumerThreads + 32), smem, stream, true, a);
+}
+
+cudaError_t launch_gemv(const GemvArgs& a, int N, cudaStream_t stream) {
+  switch (N) {
+    case 1: return launch_gemv_t<1>(a, stream);
+    case 2: return launch_gemv_t<2>(a, stream);
+    case 3: return launch_gemv_t<3>(a, stream);
+    case 4: return launch_gemv_t<4>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+void launch_gemv_generic(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K,
+                         cudaStream_t stream) {
+  int64_t warps = (int64_t)M * N;
+  int64_t grid = (warps * 32 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  launch(gemv_generic_kernel, dim3((unsigned)grid), dim3(256), 0, stream, true, W, X, Y, M, N, K);
+}
+
+}  // namespace pk
+
+namespace pk {
+void launch_gemm(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K, cudaStream_t stream);
+}
+
+extern "C" {
+
+// ffi.rs:132-140.  N <= 4: HBM-streaming GEMV; larger N (graph buckets): tensor-core GEMM.
+void gemm_graphsafe_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
+                         pk_stream stream) {
+  using namespace pk;
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  if (N > 4) {
+    launch_gemm((const bf16*)W, (const bf16*)X, (bf16*)Y, M, N, K, stream);
+    return;
+  }
+  if (!gemv_stream_supported(W, X, N, K)) {
+    launch_gemv_generic((const bf16*)W, (const bf16*)X, (bf16*)Y, M, N, K, stream);
+    return;
+  }
+  GemvArgs a{};
+  a.W = (const bf16*)W;
+  a.X = (const bf16*)X;
+  a.Y[0] = a.Y[1] = a.Y[2] = (bf16*)Y;
+  a.seg_end[0] = a.seg_end[1] = a.seg_end[2] = M;
+  a.M = M;
+  a.K = K;
+  launch_gemv(a, N, stream);
+}
+
+int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
+  using namespace pk;
+  if (!g || g->M <= 0 || g->K <= 0) return -1;
+  if (!gemv_stream_supported(g->W, g->X, g->N, g->K)) return -1;
+  if (g->x_mode == 1 && (g->hidden_out == nullptr || g->hidden_out == g->X)) return -1;
+  GemvArgs a{};
+  a.W = (const bf16*)g->W;
+  a.X = (const bf16*)g->X;
+  int end = 0;
+  for (int i = 0; i < 3; ++i) {
+    a.Y[i] = (bf16*)(g->Y[i] ? g->Y[i] : g->Y[0]);
+    end += g->seg_rows[i];
+    a.seg_end[i] = end;
+  }
+  if (end == 0) a.seg_end[0] = a.seg_end[1] = g->M;
+  a.seg_end[2] = g->M;
+  a.M = g->M;
+  a.K = g->K;
+  a.x_mode = g->x_mode;
+  a.residual = (const bf16*)g->residual;
+  a.norm_w = (const bf16*)g->norm_w;
+  a.eps = g->eps;
+  a.hidden_out = (bf16*)g->hidden_out;
+  a.normed_out = (bf16*)g->normed_out;
+  a.epi = g->epi;
+  return (int)launch_gemv(a, g->N, stream);
+}
+
+}  // extern "C"

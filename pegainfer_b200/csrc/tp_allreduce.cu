@@ -1,0 +1,247 @@
+// Tensor-parallel all-reduce over NVLink peer memory, optionally fused with the residual add +
+// RMSNorm that follows it in the layer.  This is the hook north_star asks pegainfer-comm to gain;
+// it replaces `Qwen3Model::all_reduce_hidden` (pegainfer-qwen3-4b/src/weights.rs:396-405, an
+// ncclAllReduce on the compute stream) and the fused_add_rms_norm launch after it
+// (batch_decode.rs:266-277,292 / prefill.rs:154-163).
+//
+// Decode messages are 5-8 KiB (H x 1 bf16): pure latency, so the algorithm is ONE-SHOT and
+// PUSH based: every rank stores its partial straight into every peer's staging slot (posted
+// NVLink writes, no round trip), publishes a sequence flag with release semantics, polls only
+// LOCAL flags, then reduces the `world` partials from local memory in rank order (fp32, one
+// rounding -- every rank computes the identical sum, so TP ranks never diverge).  Two staging
+// slots alternate by sequence parity: a peer can be at most one collective ahead.  The sequence
+// counter lives in device memory and is advanced by the kernel, so the launch is CUDA-graph
+// replayable.  One process per GPU: peers map each other's staging with cudaIpc handles.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pk {
+
+constexpr int kTpMaxWorld = 8;
+constexpr int kTpMaxCtas = 64;
+constexpr int kTpThreads = 512;
+
+struct TpDev {
+  uint8_t* stage[kTpMaxWorld];   // stage[p]: rank p's staging base as mapped in THIS process
+  uint32_t* flags[kTpMaxWorld];  // flags[p]: rank p's flag array  [2][kTpMaxCtas][world] + ctl
+  int rank, world;
+  int64_t slot_bytes;            // bytes per (slot, src) region
+};
+
+struct TpArgs {
+  TpDev d;
+  const bf16* partial;  // this rank's partial [T, dim]
+  bf16* hidden;         // mode 0: output of the sum (may alias partial); mode 1: residual stream
+  const bf16* weight;
+  bf16* out;
+  int dim, T, mode;
+  float eps;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a) {
+  extern __shared__ float tp_row[];  // mode 1: dim floats + 40
+  const int me = a.d.rank, W = a.d.world;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int nv = a.dim >> 3;
+  uint32_t* my_flags = a.d.flags[me];
+  uint32_t* ctl = my_flags + 2 * kTpMaxCtas * kTpMaxWorld;  // [0]=seq, [1]=done counter
+  pdl_wait();
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;
+  const int slot = (int)(seq & 1u);
+
+  // ---- push my partial into every peer's staging region [slot][me] ----
+  for (int t = c; t < a.T; t += G) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.partial + (size_t)t * a.dim);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const uint4 v = src[i];
+      for (int p = 0; p < W; ++p) {
+        if (p == me) continue;
+        uint4* dst = reinterpret_cast<uint4*>(a.d.stage[p] + (size_t)(slot * W + me) * a.d.slot_bytes +
+                                              (size_t)t * a.dim * 2);
+        dst[i] = v;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < W && (int)threadIdx.x != me) {
+    const int p = threadIdx.x;
+    st_release_sys(a.d.flags[p] + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + me, seq);
+    const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + p;
+    while (ld_acquire_sys(f) != seq) {
+    }
+  }
+  __syncthreads();
+
+  // ---- reduce in rank order from local memory ----
+  const uint8_t* local = a.d.stage[me] + (size_t)slot * W * a.d.slot_bytes;
+  float* red = tp_row + a.dim;
+  for (int t = c; t < a.T; t += G) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < W; ++r) {
+        uint4 v;
+        if (r == me)
+          v = reinterpret_cast<const uint4*>(a.partial + (size_t)t * a.dim)[i];
+        else
+          v = __ldcg(reinterpret_cast<const uint4*>(local + (size_t)r * a.d.slot_bytes +
+                                                    (size_t)t * a.dim * 2) + i);
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+      }
+      if (a.mode == 0) {
+        uint4 o;
+        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+        reinterpret_cast<uint4*>(a.hidden + (size_t)t * a.dim)[i] = o;
+      } else {
+        // the collective's result is bf16 (NCCL in place on a bf16 buffer), then
+        // fused_add_rms_norm: x = f32(hidden) + f32(sum); hidden = bf16(x); norm on unrounded x
+        const uint4 h = reinterpret_cast<const uint4*>(a.hidden + (size_t)t * a.dim)[i];
+        float x[8] = {bf16_lo(h.x) + round_bf16(acc[0]), bf16_hi(h.x) + round_bf16(acc[1]),
+                      bf16_lo(h.y) + round_bf16(acc[2]), bf16_hi(h.y) + round_bf16(acc[3]),
+                      bf16_lo(h.z) + round_bf16(acc[4]), bf16_hi(h.z) + round_bf16(acc[5]),
+                      bf16_lo(h.w) + round_bf16(acc[6]), bf16_hi(h.w) + round_bf16(acc[7])};
+        uint4 hs;
+        hs.x = pack_bf16(x[0], x[1]); hs.y = pack_bf16(x[2], x[3]);
+        hs.z = pack_bf16(x[4], x[5]); hs.w = pack_bf16(x[6], x[7]);
+        reinterpret_cast<uint4*>(a.hidden + (size_t)t * a.dim)[i] = hs;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ss = fmaf(x[j], x[j], ss);
+          tp_row[i * 8 + j] = x[j];
+        }
+      }
+    }
+    if (a.mode == 1) {
+      const float tot = block_sum(ss, red);
+      const float rinv = rsqrtf(tot / (float)a.dim + a.eps);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const uint4 g = reinterpret_cast<const uint4*>(a.weight)[i];
+        const float* x = tp_row + i * 8;
+        uint4 o;
+        o.x = pack_bf16(x[0] * rinv * bf16_lo(g.x), x[1] * rinv * bf16_hi(g.x));
+        o.y = pack_bf16(x[2] * rinv * bf16_lo(g.y), x[3] * rinv * bf16_hi(g.y));
+        o.z = pack_bf16(x[4] * rinv * bf16_lo(g.z), x[5] * rinv * bf16_hi(g.z));
+        o.w = pack_bf16(x[6] * rinv * bf16_lo(g.w), x[7] * rinv * bf16_hi(g.w));
+        reinterpret_cast<uint4*>(a.out + (size_t)t * a.dim)[i] = o;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- advance the sequence once per launch (last CTA) ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t done = atomicAdd(ctl + 1, 1u);
+    if (done == (uint32_t)G - 1) {
+      ctl[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(ctl) = seq;
+    }
+  }
+}
+
+}  // namespace pk
+
+struct pk_tp_comm {
+  pk::TpDev d;
+  int64_t staging_bytes;
+};
+
+using namespace pk;
+
+extern "C" {
+
+pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
+                              void* const* flag_ptrs, int64_t staging_bytes) {
+  if (world < 1 || world > kTpMaxWorld || rank < 0 || rank >= world) return nullptr;
+  pk_tp_comm* c = new pk_tp_comm();
+  memset(c, 0, sizeof(*c));
+  c->d.rank = rank;
+  c->d.world = world;
+  for (int p = 0; p < world; ++p) {
+    c->d.stage[p] = static_cast<uint8_t*>(staging_ptrs[p]);
+    c->d.flags[p] = static_cast<uint32_t*>(flag_ptrs[p]);
+  }
+  c->staging_bytes = staging_bytes;
+  c->d.slot_bytes = (staging_bytes / (2 * world)) & ~(int64_t)15;
+  return c;
+}
+
+void pk_tp_comm_destroy(pk_tp_comm* comm) { delete comm; }
+
+int64_t pk_tp_flag_bytes(void) { return (2 * kTpMaxCtas * kTpMaxWorld + 16) * sizeof(uint32_t); }
+
+static int tp_launch(pk_tp_comm* comm, const pk_bf16* partial, pk_bf16* hidden,
+                     const pk_bf16* weight, pk_bf16* out, int dim, int T, float eps, int mode,
+                     pk_stream stream) {
+  if (!comm || dim % 8 != 0 || T <= 0) return -1;
+  if ((int64_t)T * dim * 2 > comm->d.slot_bytes) return -2;  // caller chunks larger messages
+  TpArgs a{};
+  a.d = comm->d;
+  a.partial = (const bf16*)partial;
+  a.hidden = (bf16*)hidden;
+  a.weight = (const bf16*)weight;
+  a.out = (bf16*)out;
+  a.dim = dim; a.T = T; a.mode = mode; a.eps = eps;
+  const int grid = T < kTpMaxCtas ? T : kTpMaxCtas;
+  const size_t smem = mode == 1 ? sizeof(float) * ((size_t)dim + 40) : sizeof(float) * 40;
+  return (int)launch(tp_allreduce_kernel, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
+}
+
+int pk_tp_all_reduce(pk_tp_comm* comm, pk_bf16* hidden, int64_t n, pk_stream stream) {
+  // in-place SUM over n bf16 elements, treated as rows of <= 4096 elements
+  if (!comm || n <= 0 || n % 8 != 0) return -1;
+  int dim = (int)n, T = 1;
+  if (n > 8192) {
+    for (int cand = 8192; cand >= 8; cand -= 8)
+      if (n % cand == 0) { dim = cand; T = (int)(n / cand); break; }
+  }
+  return tp_launch(comm, hidden, hidden, nullptr, nullptr, dim, T, 0.f, 0, stream);
+}
+
+int pk_tp_all_reduce_rows(pk_tp_comm* comm, pk_bf16* hidden, int hidden_dim, int rows,
+                          pk_stream stream) {
+  return tp_launch(comm, hidden, hidden, nullptr, nullptr, hidden_dim, rows, 0.f, 0, stream);
+}
+
+int pk_tp_all_reduce_add_rms_norm(pk_tp_comm* comm, pk_bf16* hidden, const pk_bf16* partial,
+                                  const pk_bf16* weight, pk_bf16* out, int hidden_dim,
+                                  int batch_size, float eps, pk_stream stream) {
+  if (hidden_dim > 11000) return -1;  // row parked in shared memory as fp32
+  return tp_launch(comm, partial, hidden, weight, out, hidden_dim, batch_size, eps, 1, stream);
+}
+
+int64_t pk_tp_max_rows(pk_tp_comm* comm, int hidden_dim) {
+  if (!comm || hidden_dim <= 0) return 0;
+  return comm->d.slot_bytes / ((int64_t)hidden_dim * 2);
+}
+
+// cudaIpc plumbing for the one-process-per-GPU model (handles travel over torch.distributed)
+int pk_tp_ipc_export(void* dev_ptr, void* handle_out_64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle_out_64, &h, sizeof(h));
+  return 0;
+}
+int pk_tp_ipc_open(const void* handle_64, void** dev_ptr_out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int pk_tp_ipc_close(void* dev_ptr) { return (int)cudaIpcCloseMemHandle(dev_ptr); }
+
+}  // extern "C"

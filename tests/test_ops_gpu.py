@@ -1,0 +1,383 @@
+"""Op-level parity on the GPU, through the C ABI: every hot-path kernel against the CPU oracle on
+the same seeded inputs.  Each case runs twice: on libpegainfer_kernels_b200.so (the product) and,
+when oracle/_ref was built, on the reference's own CUDA kernels behind the same ABI -- the second
+run is what pins the oracle to the reference on real hardware.
+
+Tolerances (bf16 ulps at max(|want|, floor)): copies and adds are bit-exact; norm / SiLU / RoPE
+1-2 ulp (rsqrt.approx, expf, FMA contraction); GEMV / GEMM 1 ulp above a floor of max|y|/64
+(fp32 reduction order is unspecified in cuBLAS too); attention 2-3 ulp (ex2.approx, order).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen3_oracle as O
+from pegainfer_b200 import ffi
+from pegainfer_b200.paged_kv import PagedKvLayout
+from tests.helpers import assert_bf16_close, bits, from_bits, f32
+
+pytestmark = pytest.mark.gpu
+
+REF_LIB = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libkernels_ref.so")
+LIBS = ["b200"] + (["ref"] if os.path.exists(REF_LIB) else [])
+_loaded = {}
+
+
+def get_lib(kind):
+    if kind not in _loaded:
+        if kind == "b200":
+            lib = ffi.lib()
+        else:
+            lib = ffi.load(REF_LIB, extensions=False)
+        torch.cuda.init()
+        torch.zeros(1, device="cuda")
+        lib.cuda_set_device(0)
+        lib.cublas_init()
+        _loaded[kind] = lib
+    return _loaded[kind]
+
+
+@pytest.fixture(params=LIBS)
+def lib(request):
+    return get_lib(request.param)
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def p(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def i32(a):
+    return torch.tensor(np.asarray(a, dtype=np.int32), device="cuda")
+
+
+# ------------------------------------------------------------------ embedding / elementwise
+@pytest.mark.parametrize("hidden,seq", [(4, 2), (2560, 1), (2560, 37), (260, 3)])
+def test_embedding(lib, hidden, seq):
+    vocab = 97
+    embed = rnd((vocab, hidden), 1)
+    ids = torch.randint(0, vocab, (seq,), generator=torch.Generator().manual_seed(2), dtype=torch.int32)
+    out = torch.zeros((seq, hidden), dtype=torch.bfloat16, device="cuda")
+    e_d, ids_d = dev(embed), ids.cuda()
+    rc = lib.embedding_batched_cuda(p(e_d), p(ids_d), p(out), hidden, seq, stream())
+    assert rc == 0
+    want = O.embedding_batched(bits(embed), ids.numpy().astype(np.uint32), hidden)
+    assert (bits(out) == want).all()
+    out1 = torch.zeros(hidden, dtype=torch.bfloat16, device="cuda")
+    assert lib.embedding_decode_cuda(p(e_d), p(ids_d), p(out1), hidden, stream()) == 0
+    assert (bits(out1) == want[0]).all()
+
+
+def test_embedding_vocab_shard(lib):  # pegainfer-kernels/src/ops/embedding.rs:99-128
+    embed = from_bits(O.f32_to_bf16(np.array([10, 11, 12, 20, 21, 22], np.float32))).reshape(2, 3)
+    ids = torch.tensor([4, 5, 1, 4], dtype=torch.int32).cuda()
+    out = torch.zeros((4, 3), dtype=torch.bfloat16, device="cuda")
+    assert lib.embedding_batched_vocab_shard_cuda(p(dev(embed)), p(ids), p(out), 3, 4, 4, 2, stream()) == 0
+    assert out.float().cpu().flatten().tolist() == [10, 11, 12, 20, 21, 22, 0, 0, 0, 10, 11, 12]
+
+
+@pytest.mark.parametrize("n", [5, 2560, 2560 * 33 + 3])
+def test_add(lib, n):
+    a, b = rnd((n,), 3), rnd((n,), 4)
+    out = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    assert lib.add_cuda(p(dev(a)), p(dev(b)), p(out), n, stream()) == 0
+    assert (bits(out) == O.add(bits(a), bits(b))).all()
+
+
+@pytest.mark.parametrize("inter,bs", [(9728, 1), (9728, 5), (52, 3)])
+def test_silu_mul_fused(lib, inter, bs):
+    gu = rnd((bs, 2 * inter), 5, 2.0)
+    out = torch.zeros((bs, inter), dtype=torch.bfloat16, device="cuda")
+    lib.silu_mul_fused_cuda(p(dev(gu)), p(out), inter, bs, stream())
+    assert_bf16_close(bits(out), O.silu_mul_fused(bits(gu), inter), 1, floor=1e-3, frac_exact=0.98,
+                      what="silu_mul_fused")
+
+
+def test_silu_mul_rounded(lib):
+    g, u = rnd((4096,), 6, 2.0), rnd((4096,), 7)
+    out = torch.zeros(4096, dtype=torch.bfloat16, device="cuda")
+    assert lib.silu_mul_triton_aot_cuda(p(dev(g)), p(dev(u)), p(out), 4096, stream()) == 0
+    assert_bf16_close(bits(out), O.silu_mul(bits(g), bits(u)), 1, floor=1e-3, frac_exact=0.98)
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("hidden,seq", [(4, 1), (260, 2), (2560, 1), (2560, 19), (4096, 4)])
+def test_rms_norm(lib, hidden, seq):
+    x, w = rnd((seq, hidden), 8, 3.0), rnd((hidden,), 9, 0.2) + 1
+    out = torch.zeros_like(x, device="cuda")
+    lib.rms_norm_batched_cuda(p(dev(x)), p(dev(w)), p(out), hidden, seq, 1e-6, stream())
+    assert_bf16_close(bits(out), O.rms_norm(bits(x), bits(w), 1e-6), 1, frac_exact=0.97, what="rms_norm")
+    if seq == 1:
+        out1 = torch.zeros_like(x, device="cuda")
+        lib.rms_norm_cuda(p(dev(x)), p(dev(w)), p(out1), hidden, 1e-6, stream())
+        assert (bits(out1) == bits(out)).all()
+
+
+def test_rms_norm_reference_known_answers(lib):  # ops/tests.rs:88-152
+    x = from_bits(O.f32_to_bf16(np.array([1, 2, 3, 4], np.float32)))
+    w = from_bits(O.f32_to_bf16(np.ones(4, np.float32)))
+    out = torch.zeros(4, dtype=torch.bfloat16, device="cuda")
+    lib.rms_norm_cuda(p(dev(x)), p(dev(w)), p(out), 4, 1e-6, stream())
+    inv = 1.0 / math.sqrt((1 + 4 + 9 + 16) / 4 + 1e-6)
+    assert np.abs(out.float().cpu().numpy() - np.array([1, 2, 3, 4]) * inv).max() <= 0.01
+
+
+@pytest.mark.parametrize("hidden,bs", [(2560, 1), (2560, 7), (4096, 2), (260, 3)])
+def test_fused_add_rms_norm(lib, hidden, bs):
+    h, r, w = rnd((bs, hidden), 10, 2.0), rnd((bs, hidden), 11, 0.5), rnd((hidden,), 12, 0.2) + 1
+    h_d, out = dev(h), torch.zeros((bs, hidden), dtype=torch.bfloat16, device="cuda")
+    lib.fused_add_rms_norm_batched_cuda(p(h_d), p(dev(r)), p(dev(w)), p(out), hidden, bs, 1e-6, stream())
+    h_np = bits(h).copy()
+    want = O.fused_add_rms_norm(h_np, bits(r), bits(w), 1e-6)
+    assert (bits(h_d) == h_np).all(), "hidden += residual must be bit-exact"
+    assert_bf16_close(bits(out), want, 1, frac_exact=0.97, what="fused_add_rms_norm")
+
+
+# ------------------------------------------------------------------ GEMV / GEMM
+def test_gemv_known_answer(lib):  # ops/tests.rs:50-77
+    a = from_bits(O.f32_to_bf16(np.array([1, 2, 3, 4, 5, 6], np.float32))).reshape(2, 3)
+    x = from_bits(O.f32_to_bf16(np.array([1, 2, 3], np.float32)))
+    y = torch.zeros(2, dtype=torch.bfloat16, device="cuda")
+    lib.gemm_graphsafe_cuda(p(dev(a)), p(dev(x)), p(y), 2, 1, 3, stream())
+    assert y.float().cpu().tolist() == [14.0, 32.0]
+
+
+@pytest.mark.parametrize("M,K", [(1024, 2560), (2560, 9728), (6144, 2560), (151936 // 8, 2560), (333, 1288)])
+def test_gemv_stream(lib, M, K):
+    W, x = rnd((M, K), 13, 0.02), rnd((1, K), 14, 1.0)
+    y = torch.zeros((1, M), dtype=torch.bfloat16, device="cuda")
+    lib.gemm_graphsafe_cuda(p(dev(W)), p(dev(x)), p(y), M, 1, K, stream())
+    want = O.gemm(bits(W), bits(x))
+    floor = float(np.abs(f32(want)).max()) / 64
+    assert_bf16_close(bits(y), want, 1, floor=floor, frac_exact=0.9, what=f"gemv {M}x{K}")
+
+
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_gemv_multi_token(lib, N):
+    M, K = 2048, 2560
+    W, x = rnd((M, K), 15, 0.02), rnd((N, K), 16, 1.0)
+    y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
+    lib.gemm_graphsafe_cuda(p(dev(W)), p(dev(x)), p(y), M, N, K, stream())
+    want = O.gemm(bits(W), bits(x))
+    assert_bf16_close(bits(y), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 128, 2560), (2560, 77, 4096), (1000, 130, 576), (4096, 300, 2560),
+                                   (19456, 128, 2560), (64, 8, 64), (24, 16, 40)])
+def test_gemm(lib, M, N, K):
+    W, X = rnd((M, K), 17, 0.02), rnd((N, K), 18, 1.0)
+    Y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
+    lib.gemm_cuda(p(dev(W)), p(dev(X)), p(Y), M, N, K, stream())
+    torch.cuda.synchronize()
+    want = O.gemm(bits(W), bits(X))
+    assert_bf16_close(bits(Y), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9,
+                      what=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_graphsafe_batch_bucket(lib):  # decode bucket > 4 goes to the tensor-core path
+    M, N, K = 2560, 8, 2560
+    W, X = rnd((M, K), 19, 0.02), rnd((N, K), 20, 1.0)
+    Y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
+    lib.gemm_graphsafe_cuda(p(dev(W)), p(dev(X)), p(Y), M, N, K, stream())
+    want = O.gemm(bits(W), bits(X))
+    assert_bf16_close(bits(Y), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9)
+
+
+# ------------------------------------------------------------------ QK norm + RoPE
+@pytest.mark.parametrize("tokens,nq,nkv,decode", [(1, 32, 8, True), (5, 32, 8, True), (37, 32, 8, False), (3, 4, 1, True)])
+def test_qk_norm_rope(lib, tokens, nq, nkv, decode):
+    hd = 128
+    q, k = rnd((tokens, nq * hd), 21, 2.0), rnd((tokens, nkv * hd), 22, 2.0)
+    qw, kw = rnd((hd,), 23, 0.3) + 1, rnd((hd,), 24, 0.3) + 1
+    cos, sin = O.precompute_rope(hd, 4096, 1e6)
+    q_d, k_d = dev(q), dev(k)
+    cos_d, sin_d = from_bits(cos, "cuda"), from_bits(sin, "cuda")
+    qn, kn = bits(q).copy(), bits(k).copy()
+    if decode:
+        pos = np.array([(17 * i + 3) % 4096 for i in range(tokens)], np.int32)
+        lib.qk_norm_rope_batched_decode_cuda(p(q_d), p(k_d), p(dev(qw)), p(dev(kw)), p(cos_d), p(sin_d),
+                                             p(i32(pos)), nq, nkv, hd, tokens, 1e-6, stream())
+        O.qk_norm_rope(qn, kn, bits(qw), bits(kw), cos, sin, nq, nkv, hd, 1e-6, positions=pos)
+    else:
+        lib.prefill_qk_norm_rope_only_cuda(p(q_d), p(k_d), p(dev(qw)), p(dev(kw)), p(cos_d), p(sin_d),
+                                           nq, nkv, hd, tokens, 11, 1e-6, stream())
+        O.qk_norm_rope(qn, kn, bits(qw), bits(kw), cos, sin, nq, nkv, hd, 1e-6, start_pos=11)
+    assert_bf16_close(bits(q_d), qn, 2, floor=2 ** -6, frac_exact=0.9, what="q rope")
+    assert_bf16_close(bits(k_d), kn, 2, floor=2 ** -6, frac_exact=0.9, what="k rope")
+
+
+# ------------------------------------------------------------------ paged KV + attention
+class Paged:
+    """Synthetic paged pool for one layer-agnostic test: L layers, shuffled page ids."""
+
+    def __init__(self, seq_lens, nkv, num_layers=2, seed=0, fill=True):
+        self.layout = PagedKvLayout.new(num_layers, nkv, 128, 16)
+        rng = np.random.RandomState(seed)
+        need = [-(-s // 16) for s in seq_lens]
+        total = sum(need) + 3
+        ids = rng.permutation(np.arange(1, total + 1))
+        self.page_indices, self.indptr, self.last = [], [0], []
+        off = 0
+        for s, n in zip(seq_lens, need):
+            self.page_indices += ids[off:off + n].tolist()
+            off += n
+            self.indptr.append(len(self.page_indices))
+            self.last.append(((s - 1) % 16) + 1 if s else 0)
+        self.num_pages = total + 1
+        g = torch.Generator().manual_seed(seed + 100)
+        n_el = self.num_pages * self.layout.page_stride
+        self.kv = (torch.randn(n_el, generator=g) * (1.0 if fill else 0.0)).to(torch.bfloat16)
+        self.pi = np.array(self.page_indices, np.int32)
+        self.ip = np.array(self.indptr, np.int32)
+        self.lpl = np.array(self.last, np.int32)
+
+
+@pytest.mark.parametrize("nkv", [8, 1])
+def test_paged_kv_scatter(lib, nkv):
+    hd, seq_lens, layer = 128, [40, 7, 16], 1
+    pg = Paged(seq_lens, nkv, fill=False)
+    L = pg.layout
+    toks = [(b, t) for b, s in enumerate(seq_lens) for t in range(s) if (t * 7 + b) % 3 != 0]
+    bidx = np.array([b for b, _ in toks], np.int32)
+    pos = np.array([t for _, t in toks], np.int32)
+    k, v = rnd((len(toks), nkv * hd), 30), rnd((len(toks), nkv * hd), 31)
+    kv_d = dev(pg.kv)
+    rc = lib.paged_kv_scatter_cuda(p(kv_d), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)), p(i32(pg.ip)),
+                                   p(i32(pg.lpl)), p(dev(k)), p(dev(v)), p(i32(bidx)), p(i32(pos)), len(toks),
+                                   nkv, hd, 16, L.page_stride, nkv * hd, hd, stream())
+    assert rc == 0
+    want = bits(pg.kv).copy()
+    O.paged_kv_scatter(want, L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl, bits(k), bits(v),
+                       bidx, pos, nkv, hd, 16, L.page_stride)
+    assert (bits(kv_d) == want).all()
+
+
+@pytest.mark.parametrize("seq_lens,nq,nkv", [([1], 32, 8), ([128], 32, 8), ([191, 33, 1], 32, 8), ([700], 4, 1),
+                                             ([1500, 900], 32, 8)])
+def test_paged_attention_decode(lib, seq_lens, nq, nkv):
+    hd, layer, bs = 128, 1, len(seq_lens)
+    pg = Paged(seq_lens, nkv, seed=3)
+    L = pg.layout
+    q = rnd((bs, nq * hd), 32)
+    out = torch.zeros((bs, nq * hd), dtype=torch.bfloat16, device="cuda")
+    req, tile0, chunk = np.arange(bs, dtype=np.int32), np.zeros(bs, np.int32), np.array(seq_lens, np.int32)
+    sm = 1 / math.sqrt(hd)
+    rc = lib.paged_attention_decode_cuda(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
+                                         p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(req)), p(i32(tile0)),
+                                         p(i32(chunk)), nq, nkv, hd, 16, bs, L.page_stride, sm, stream())
+    assert rc == 0
+    want = O.paged_attention_decode(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip,
+                                    pg.lpl, req, tile0, chunk, nq, nkv, hd, 16, L.page_stride, sm)
+    assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="decode attn")
+
+
+@pytest.mark.parametrize("seq_lens", [[1024], [2300, 1100]])
+def test_paged_attention_decode_split_kv(lib, seq_lens):
+    nq, nkv, hd, layer, bs = 32, 8, 128, 0, len(seq_lens)
+    pg = Paged(seq_lens, nkv, seed=4)
+    L = pg.layout
+    q = rnd((bs, nq * hd), 33)
+    csz = max(256, -(-max(seq_lens) // 64))
+    sreq, stile, mask, oip = [], [], [], [0]
+    for b, s in enumerate(seq_lens):
+        n = max(1, -(-s // csz))
+        sreq += [b] * n; stile += list(range(n)); mask += [1] * n; oip.append(len(sreq))
+    pad = bs * 64 - len(sreq)
+    sreq += [0] * pad; stile += [0] * pad; mask += [0] * pad
+    sreq, stile = np.array(sreq, np.int32), np.array(stile, np.int32)
+    mask, oip, csz_a = np.array(mask, np.uint8), np.array(oip, np.int32), np.array([csz], np.int32)
+    slots = len(sreq)
+    out = torch.zeros((bs, nq * hd), dtype=torch.bfloat16, device="cuda")
+    tmp_v = torch.zeros((slots, nq * hd), dtype=torch.bfloat16, device="cuda")
+    tmp_s = torch.zeros((slots, nq), dtype=torch.float32, device="cuda")
+    sm = 1 / math.sqrt(hd)
+    rc = lib.paged_attention_decode_split_kv_cuda(
+        p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)), p(i32(pg.ip)),
+        p(i32(pg.lpl)), p(i32(sreq)), p(i32(stile)), p(i32(csz_a)), p(i32(oip)),
+        p(torch.tensor(mask, device="cuda")), p(tmp_v), p(tmp_s), nq, nkv, hd, 16, bs, slots, L.page_stride, sm,
+        stream())
+    assert rc == 0
+    want = O.paged_attention_decode_split_kv(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi,
+                                             pg.ip, pg.lpl, sreq, stile, csz_a, oip, mask, nq, nkv, hd, 16, bs,
+                                             L.page_stride, sm)
+    assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="split-kv attn")
+
+
+@pytest.mark.parametrize("starts,lens,nq,nkv", [([0], [128], 32, 8), ([0], [77], 32, 8), ([0, 0, 0], [33, 100, 5], 32, 8),
+                                                ([40], [60], 32, 8), ([0], [300], 4, 1)])
+def test_batch_prefill_paged(lib, starts, lens, nq, nkv):
+    hd, layer, bs = 128, 1, len(lens)
+    kv_lens = [s + n for s, n in zip(starts, lens)]
+    pg = Paged(kv_lens, nkv, seed=5)
+    L = pg.layout
+    T = sum(lens)
+    q = rnd((T, nq * hd), 34)
+    out = torch.zeros((T, nq * hd), dtype=torch.bfloat16, device="cuda")
+    q_indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    group = nq // nkv
+    tile_q = lib.batch_prefill_cta_tile_q_with_override(T, nq, nkv, hd, 64)
+    assert tile_q == 64
+    ri, qti = [], []
+    for b, n in enumerate(lens):
+        for t in range(-(-n * group // tile_q)):
+            ri.append(b); qti.append(t)
+    nt = len(ri)
+    sm = 1 / math.sqrt(hd)
+    rc = lib.batch_prefill_paged_cuda_with_cta_tile_q(
+        p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)), p(i32(pg.ip)),
+        p(i32(pg.lpl)), p(i32(q_indptr)), p(i32(ri)), p(i32(qti)), p(i32(np.zeros(nt))), p(i32(kv_lens)),
+        p(torch.tensor([T], dtype=torch.int32, device="cuda")), nq, nkv, hd, 16, T, bs, nt, L.page_stride, sm, 64,
+        stream())
+    assert rc == 0
+    want = O.batch_prefill_paged(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl,
+                                 q_indptr, nq, nkv, hd, 16, L.page_stride, sm)
+    assert_bf16_close(bits(out), want, 4, floor=float(np.abs(f32(want)).max()) / 32, what="prefill attn")
+
+
+def test_prefill_planner_helpers(lib):  # csrc/paged_attention.cu:343-397
+    assert lib.batch_prefill_cta_tile_q(2048, 32, 8, 128) == 128
+    assert lib.batch_prefill_cta_tile_q(8, 32, 8, 128) == 64
+    assert lib.batch_prefill_cta_tile_q(2, 32, 8, 128) == 16
+    assert lib.batch_prefill_cta_tile_q_with_override(2048, 32, 8, 128, 64) == 64
+    assert lib.batch_prefill_cta_tile_q_with_override(2048, 32, 8, 128, 48) == 0
+    assert lib.batch_prefill_paged_num_tiles_with_cta_tile_q(2048, 32, 8, 128, 64) == 128
+    assert lib.batch_prefill_paged_num_tiles_with_cta_tile_q(2048, 32, 8, 128, 48) == -1
+    assert lib.batch_prefill_paged_num_tiles(100, 32, 8, 128) == 4
+
+
+# ------------------------------------------------------------------ sampling
+def test_argmax_known_answer(lib):  # ops/tests.rs:79-86
+    x = from_bits(O.f32_to_bf16(np.array([1.0, 9.0, 3.0, 8.0], np.float32)), "cuda")
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lib.argmax_cuda(p(x), p(out), 4, stream())
+    assert int(out.item()) == 1
+
+
+@pytest.mark.parametrize("n", [5, 1000, 151936])
+def test_top1_matches_argmax(lib, n):
+    x = rnd((n,), 40, 3.0)
+    want = O.argmax(bits(x))
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lib.argmax_cuda(p(dev(x)), p(out), n, stream())
+    assert int(out.item()) == want
+    val = torch.zeros(8, dtype=torch.bfloat16, device="cuda")
+    states = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):  # twice: the scratch must be left reusable
+        out.zero_()
+        lib.flashinfer_top1_cuda(p(dev(x)), p(val), p(states), p(out), n, stream())
+        assert int(out.item()) == want
