@@ -1,0 +1,195 @@
+"""Python front end of the C++ host mirror (``libpegainfer_qwen3_host.so``).
+
+Mirrors the reference's executor-facing surface for the hot path
+(pegainfer-qwen3-4b/src/executor.rs:541-640 ``Qwen3Executor::{from_runtime, execute_prefill,
+execute_decode, drop_request}``): create a model from a checkpoint dict, allocate per-request KV
+state, run prefill / decode steps, sample greedily.  All compute happens in the sm_100a kernels
+behind the pegainfer-kernels C ABI; there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import torch
+
+from . import ffi
+from .config import Qwen3Config, TensorParallelConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libpegainfer_qwen3_host.so")
+
+
+class _PqConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("hidden_size", "intermediate_size", "num_hidden_layers",
+                                       "num_attention_heads", "num_key_value_heads", "head_dim", "vocab_size")] + \
+               [("rms_norm_eps", C.c_float), ("rope_theta", C.c_float), ("tie_word_embeddings", C.c_int)]
+
+
+class _PqRuntime(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("device_ordinal", "tp_rank", "tp_world", "enable_cuda_graph", "mode",
+                                       "num_pages", "max_batch", "enable_pdl")]
+
+
+_host = None
+
+
+def host_lib() -> C.CDLL:
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise OSError(f"{HOST_LIB_PATH} not found: run `python -m pegainfer_b200.build`")
+        h = C.CDLL(HOST_LIB_PATH)
+        vp, i32 = C.c_void_p, C.c_int
+        h.pq_create_error.restype = C.c_char_p
+        h.pq_model_create.restype = vp
+        h.pq_model_create.argtypes = [C.POINTER(_PqConfig), C.POINTER(_PqRuntime), C.c_char_p, vp]
+        h.pq_model_destroy.argtypes = [vp]
+        h.pq_last_error.restype = C.c_char_p
+        h.pq_last_error.argtypes = [vp]
+        h.pq_model_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, i32]
+        h.pq_model_finalize.argtypes = [vp]
+        h.pq_stream.restype = vp
+        h.pq_stream.argtypes = [vp]
+        h.pq_kv_alloc.argtypes = [vp]
+        h.pq_kv_free.argtypes = [vp, i32]
+        h.pq_kv_seq_len.argtypes = [vp, i32]
+        h.pq_available_pages.argtypes = [vp]
+        h.pq_prefill.argtypes = [vp, i32, vp, vp, vp, vp]
+        h.pq_decode.argtypes = [vp, i32, vp, vp, vp, vp]
+        h.pq_sample_greedy.argtypes = [vp, vp, vp]
+        h.pq_sync.argtypes = [vp]
+        h.pq_copy_out.argtypes = [vp, vp, vp, C.c_int64]
+        h.pq_launch_count.restype = C.c_int64
+        h.pq_launch_count.argtypes = [vp, i32]
+        h.pq_debug_buffer.restype = vp
+        h.pq_debug_buffer.argtypes = [vp, C.c_char_p]
+        h.pq_generate.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        _host = h
+    return _host
+
+
+@dataclass
+class ModelRuntimeConfig:
+    """weights.rs:13-29 ``ModelRuntimeConfig`` plus the B200 switches."""
+    enable_cuda_graph: bool = True
+    tensor_parallel: TensorParallelConfig = TensorParallelConfig()
+    device_ordinal: int = 0
+    fused: bool = True          # False: the reference's op sequence through the ffi.rs ABI only
+    num_pages: int = 0          # 0: 85 % of free memory
+    max_batch: int = 4
+    enable_pdl: bool = True
+    kernel_lib: str | None = None  # default: libpegainfer_kernels_b200.so
+
+
+class Qwen3Model:
+    def __init__(self, cfg: Qwen3Config, weights: dict[str, torch.Tensor],
+                 runtime: ModelRuntimeConfig | None = None, tp_comm: int | None = None):
+        rt = runtime or ModelRuntimeConfig()
+        rt.tensor_parallel.validate_for(cfg)
+        if not torch.cuda.is_available():
+            raise RuntimeError("pegainfer_b200 needs a CUDA device (there is no CPU path)")
+        self.cfg, self.rt = cfg, rt
+        self._h = host_lib()
+        pc = _PqConfig(cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                       cfg.num_key_value_heads, cfg.head_dim, cfg.vocab_size, cfg.rms_norm_eps, cfg.rope_theta,
+                       int(cfg.tie_word_embeddings))
+        pr = _PqRuntime(rt.device_ordinal, rt.tensor_parallel.rank, rt.tensor_parallel.world_size,
+                        int(rt.enable_cuda_graph), 1 if rt.fused else 0, rt.num_pages, rt.max_batch,
+                        int(rt.enable_pdl))
+        lib_path = rt.kernel_lib or ffi.KERNEL_LIB_PATH
+        torch.cuda.set_device(rt.device_ordinal)
+        self._m = self._h.pq_model_create(C.byref(pc), C.byref(pr), lib_path.encode(), tp_comm)
+        if not self._m:
+            raise RuntimeError("pq_model_create: " + self._h.pq_create_error().decode())
+        for name, t in weights.items():
+            if name == "lm_head.weight" and cfg.tie_word_embeddings:
+                continue
+            assert t.dtype == torch.bfloat16 and t.is_contiguous(), name
+            rows, cols = (t.shape[0], t.shape[1]) if t.dim() == 2 else (1, t.shape[0])
+            self._ck(self._h.pq_model_load_tensor(self._m, name.encode(), t.data_ptr(), rows, cols))
+        self._ck(self._h.pq_model_finalize(self._m))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self._h.pq_last_error(self._m).decode())
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._h.pq_model_destroy(self._m)
+            self._m = None
+
+    __del__ = close
+
+    # -- request state (executor.rs: alloc on first prefill, drop_request) --
+    def alloc_kv(self) -> int:
+        return self._h.pq_kv_alloc(self._m)
+
+    def drop_request(self, kv_id: int) -> None:
+        self._h.pq_kv_free(self._m, kv_id)
+
+    def kv_seq_len(self, kv_id: int) -> int:
+        return self._h.pq_kv_seq_len(self._m, kv_id)
+
+    def available_pages(self) -> int:
+        return self._h.pq_available_pages(self._m)
+
+    def _logits_view(self, ptr: int, rows: int) -> torch.Tensor:
+        out = torch.empty((rows, self.cfg.vocab_size), dtype=torch.bfloat16, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        self._ck(self._h.pq_copy_out(self._m, out.data_ptr(), ptr, out.numel() * 2))
+        return out
+
+    # -- execute_prefill: last-token logits per request, bf16 [n_req, vocab] --
+    def prefill(self, prompts: list[list[int]], kv_ids: list[int]) -> torch.Tensor:
+        n = len(prompts)
+        flat = [t for p in prompts for t in p]
+        toks = (C.c_uint32 * len(flat))(*flat)
+        lens = (C.c_int * n)(*[len(p) for p in prompts])
+        ids = (C.c_int * n)(*kv_ids)
+        outs = (C.c_void_p * n)()
+        self._ck(self._h.pq_prefill(self._m, n, toks, lens, ids, outs))
+        return torch.cat([self._logits_view(outs[i], 1) for i in range(n)], dim=0)
+
+    # -- execute_decode: one token per request; returns (logits [bs, vocab], greedy tokens) --
+    def decode(self, tokens: list[int], kv_ids: list[int], want_logits: bool = True):
+        bs = len(tokens)
+        toks = (C.c_uint32 * bs)(*tokens)
+        ids = (C.c_int * bs)(*kv_ids)
+        lg = C.c_void_p()
+        sampled = (C.c_int * bs)()
+        self._ck(self._h.pq_decode(self._m, bs, toks, ids, C.byref(lg), sampled))
+        logits = self._logits_view(lg.value, bs) if want_logits else None
+        return logits, list(sampled)
+
+    def sample_greedy(self, logits_row: torch.Tensor) -> int:
+        out = C.c_int()
+        self._ck(self._h.pq_sample_greedy(self._m, logits_row.data_ptr(), C.byref(out)))
+        return out.value
+
+    def generate(self, prompt: list[int], max_tokens: int):
+        """Greedy generation timed like bench_serving.rs: returns (tokens, ttft_ms, step_ms[])."""
+        toks = (C.c_uint32 * len(prompt))(*prompt)
+        out = (C.c_uint32 * max_tokens)()
+        ttft = C.c_double()
+        steps = (C.c_double * max(1, max_tokens - 1))()
+        self._ck(self._h.pq_generate(self._m, toks, len(prompt), max_tokens, out, C.byref(ttft), steps))
+        return list(out), ttft.value, list(steps)[:max_tokens - 1]
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self._h.pq_launch_count(self._m, int(reset)))
+
+    def sync(self):
+        self._ck(self._h.pq_sync(self._m))
+
+    @property
+    def stream(self) -> int:
+        return self._h.pq_stream(self._m)
+
+    def debug_buffer(self, name: str, numel: int) -> torch.Tensor:
+        ptr = self._h.pq_debug_buffer(self._m, name.encode())
+        out = torch.empty(numel, dtype=torch.bfloat16, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        self._ck(self._h.pq_copy_out(self._m, out.data_ptr(), ptr, numel * 2))
+        return out

@@ -50,8 +50,21 @@ def rnd(shape, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
 
 
+_keep = []  # device tensors must outlive the launches that read them (raw pointers cross the ABI)
+
+
+@pytest.fixture(autouse=True)
+def _keepalive():
+    _keep.clear()
+    yield
+    torch.cuda.synchronize()
+    _keep.clear()
+
+
 def dev(t):
-    return t.cuda().contiguous()
+    d = t.cuda().contiguous()
+    _keep.append(d)
+    return d
 
 
 def p(t):
@@ -63,7 +76,9 @@ def stream():
 
 
 def i32(a):
-    return torch.tensor(np.asarray(a, dtype=np.int32), device="cuda")
+    d = torch.tensor(np.asarray(a, dtype=np.int32), device="cuda")
+    _keep.append(d)
+    return d
 
 
 # ------------------------------------------------------------------ embedding / elementwise
@@ -73,7 +88,7 @@ def test_embedding(lib, hidden, seq):
     embed = rnd((vocab, hidden), 1)
     ids = torch.randint(0, vocab, (seq,), generator=torch.Generator().manual_seed(2), dtype=torch.int32)
     out = torch.zeros((seq, hidden), dtype=torch.bfloat16, device="cuda")
-    e_d, ids_d = dev(embed), ids.cuda()
+    e_d, ids_d = dev(embed), dev(ids)
     rc = lib.embedding_batched_cuda(p(e_d), p(ids_d), p(out), hidden, seq, stream())
     assert rc == 0
     want = O.embedding_batched(bits(embed), ids.numpy().astype(np.uint32), hidden)
@@ -85,7 +100,7 @@ def test_embedding(lib, hidden, seq):
 
 def test_embedding_vocab_shard(lib):  # pegainfer-kernels/src/ops/embedding.rs:99-128
     embed = from_bits(O.f32_to_bf16(np.array([10, 11, 12, 20, 21, 22], np.float32))).reshape(2, 3)
-    ids = torch.tensor([4, 5, 1, 4], dtype=torch.int32).cuda()
+    ids = dev(torch.tensor([4, 5, 1, 4], dtype=torch.int32))
     out = torch.zeros((4, 3), dtype=torch.bfloat16, device="cuda")
     assert lib.embedding_batched_vocab_shard_cuda(p(dev(embed)), p(ids), p(out), 3, 4, 4, 2, stream()) == 0
     assert out.float().cpu().flatten().tolist() == [10, 11, 12, 20, 21, 22, 0, 0, 0, 10, 11, 12]
@@ -309,7 +324,7 @@ def test_paged_attention_decode_split_kv(lib, seq_lens):
     rc = lib.paged_attention_decode_split_kv_cuda(
         p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)), p(i32(pg.ip)),
         p(i32(pg.lpl)), p(i32(sreq)), p(i32(stile)), p(i32(csz_a)), p(i32(oip)),
-        p(torch.tensor(mask, device="cuda")), p(tmp_v), p(tmp_s), nq, nkv, hd, 16, bs, slots, L.page_stride, sm,
+        p(dev(torch.tensor(mask))), p(tmp_v), p(tmp_s), nq, nkv, hd, 16, bs, slots, L.page_stride, sm,
         stream())
     assert rc == 0
     want = O.paged_attention_decode_split_kv(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi,
@@ -341,7 +356,7 @@ def test_batch_prefill_paged(lib, starts, lens, nq, nkv):
     rc = lib.batch_prefill_paged_cuda_with_cta_tile_q(
         p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)), p(i32(pg.ip)),
         p(i32(pg.lpl)), p(i32(q_indptr)), p(i32(ri)), p(i32(qti)), p(i32(np.zeros(nt))), p(i32(kv_lens)),
-        p(torch.tensor([T], dtype=torch.int32, device="cuda")), nq, nkv, hd, 16, T, bs, nt, L.page_stride, sm, 64,
+        p(i32([T])), nq, nkv, hd, 16, T, bs, nt, L.page_stride, sm, 64,
         stream())
     assert rc == 0
     want = O.batch_prefill_paged(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl,
