@@ -222,6 +222,11 @@ struct Qwen3Model {
   bool create_decode_buffers();
   bool prefill(int n_req, const uint32_t* tokens, const int* lens, const int* kv_ids, void** logits_out);
   bool decode(int bs, const uint32_t* tokens, const int* kv_ids, void** logits_out, int* sampled);
+  bool build_step_meta(int bs, int padded, const uint32_t* tokens, const int* kv_ids, int* mh, bool* split_out);
+  bool run_step_kernels(int padded, bool split);
+  bool decode_burst(int kv_id, uint32_t first_token, int K, uint32_t* tokens_out, float* ms_total);
+  bool bench_gemv_pass(int iters, float* ms_per_pass, int* launches_per_pass);
+  int64_t launches_per_step = 0;
   bool decode_kernels_compat(int bs, bool split);
   bool decode_kernels_fused(int bs);
   bool ensure_capacity(KvState& s, int tokens);
@@ -711,13 +716,11 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
   return true;
 }
 
-bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void** logits_out, int* sampled) {
-  if (!finalized) return fail("model not finalized");
-  if (bs <= 0 || bs > max_bs) return fail("batch size out of range");
+// Advance the KV states by one token and write the step's packed metadata block into `mh`
+// (batch_decode.rs:26-59 + sync_paged_meta / sync_split_kv_meta of batch_decode_buffers.rs:177-279).
+bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, const int* kv_ids, int* mh,
+                                 bool* split_out) {
   const bool fused = rt.mode == 1;
-  if (fused && bs > 4) return fail("fused decode path supports batch <= 4 (use mode 0)");
-  int* mh = static_cast<int*>(meta_h);
-  // advance KV (batch_decode.rs:26-34)
   std::vector<int> positions(bs);
   for (int b = 0; b < bs; ++b) {
     if (kv_ids[b] < 0 || kv_ids[b] >= (int)kv_states.size() || !kv_states[kv_ids[b]].live) return fail("bad kv id");
@@ -727,9 +730,6 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
     if (!ensure_capacity(s, s.seq_len + 1)) return false;
     s.seq_len += 1;
   }
-  const int padded = (rt.enable_cuda_graph && !fused) ? bucket_for(bs) : bs;
-  if (padded < 0 || padded > max_bs) return fail("batch exceeds max_batch bucket");
-  // ---- sync_paged_meta (batch_decode_buffers.rs:177-227) into the packed host block ----
   memset(mh, 0, meta_bytes);
   int np = 0;
   max_seq_len_step = 0;
@@ -742,7 +742,7 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
       np += (int)s.pages.size();
       mh[mo.last_page_len + b] = s.last_page_len(kPageSize);
       mh[mo.kv_chunk_size + b] = s.seq_len;
-      mh[mo.token_ids + b] = (int)tokens[b];
+      mh[mo.token_ids + b] = tokens ? (int)tokens[b] : 0;
       mh[mo.positions + b] = positions[b];
       max_seq_len_step = std::max(max_seq_len_step, s.seq_len);
     } else {  // padding slot: the padding page, seq_len 1
@@ -753,7 +753,6 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
     mh[mo.page_indptr + b + 1] = np;
     mh[mo.request_indices + b] = b;
   }
-  // ---- sync_split_kv_meta (batch_decode_buffers.rs:229-279) ----
   const bool split = !fused && padded <= kSplitMaxBs && max_seq_len_step >= kSplitMinSeq;
   {
     const int chunk = std::max(kSplitChunkTokens, (max_seq_len_step + kSplitMaxChunks - 1) / kSplitMaxChunks);
@@ -774,32 +773,50 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
     for (int b = bs; b < padded; ++b) mh[mo.split_o_indptr + b + 1] = ns;
     mh[mo.split_chunk] = chunk;
   }
+  *split_out = split;
+  return true;
+}
+
+// CudaGraphState::run_or_capture (cuda_graph.rs:28-58) around the decode body
+bool Qwen3Model::run_step_kernels(int padded, bool split) {
+  const bool fused = rt.mode == 1;
+  cudaStream_t st = ctx.stream;
+  auto body = [&]() { return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split); };
+  if (!rt.enable_cuda_graph) return body();
+  const int key = padded * 4 + (fused ? 2 : (split ? 1 : 0));
+  auto& g = graphs[key];
+  if (!g) g.reset(new CudaGraphState());
+  if (!g->captured()) {
+    const int64_t before = k.pk_b200_launch_count ? k.pk_b200_launch_count(0) : 0;
+    if (!cu(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return false;
+    const bool ok = body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (!ok) {
+      if (graph) cudaGraphDestroy(graph);
+      return false;
+    }
+    if (!cu(e, "end capture")) return false;
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (!cu(e, "graph instantiate")) return false;
+    if (k.pk_b200_launch_count) launches_per_step = k.pk_b200_launch_count(0) - before;
+  }
+  return cu(cudaGraphLaunch(g->exec, st), "graph launch");
+}
+
+bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void** logits_out, int* sampled) {
+  if (!finalized) return fail("model not finalized");
+  if (bs <= 0 || bs > max_bs) return fail("batch size out of range");
+  const bool fused = rt.mode == 1;
+  if (fused && bs > 4) return fail("fused decode path supports batch <= 4 (use mode 0)");
+  const int padded = (rt.enable_cuda_graph && !fused) ? bucket_for(bs) : bs;
+  if (padded < 0 || padded > max_bs) return fail("batch exceeds max_batch bucket");
+  bool split = false;
+  if (!build_step_meta(bs, padded, tokens, kv_ids, static_cast<int*>(meta_h), &split)) return false;
   cudaStream_t st = ctx.stream;
   if (!cu(cudaMemcpyAsync(meta_d.ptr, meta_h, meta_bytes, cudaMemcpyHostToDevice, st), "meta H2D")) return false;
-
-  auto body = [&]() { return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split); };
-  if (rt.enable_cuda_graph) {
-    const int key = padded * 4 + (fused ? 2 : (split ? 1 : 0));
-    auto& g = graphs[key];
-    if (!g) g.reset(new CudaGraphState());
-    if (!g->captured()) {  // CudaGraphState::run_or_capture (cuda_graph.rs:28-58)
-      if (!cu(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return false;
-      const bool ok = body();
-      cudaGraph_t graph = nullptr;
-      cudaError_t e = cudaStreamEndCapture(st, &graph);
-      if (!ok) {
-        if (graph) cudaGraphDestroy(graph);
-        return false;
-      }
-      if (!cu(e, "end capture")) return false;
-      e = cudaGraphInstantiate(&g->exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (!cu(e, "graph instantiate")) return false;
-    }
-    if (!cu(cudaGraphLaunch(g->exec, st), "graph launch")) return false;
-  } else if (!body()) {
-    return false;
-  }
+  if (!run_step_kernels(padded, split)) return false;
   if (logits_out) *logits_out = logits.data.ptr;
   if (sampled) {
     if (fused) {
@@ -813,6 +830,103 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
     }
   }
   return true;
+}
+
+// K greedy decode steps of ONE request with everything resident in HBM: the per-step metadata blocks
+// are staged on the device up front, each step's token id is the previous step's on-device arg-max,
+// and there is no host synchronisation inside the timed region (CUDA events on the launch stream).
+bool Qwen3Model::decode_burst(int kv_id, uint32_t first_token, int K, uint32_t* tokens_out, float* ms_total) {
+  if (!finalized || rt.mode != 1) return fail("decode_burst needs the fused path");
+  if (K <= 0) return fail("K must be positive");
+  DeviceBuf staged;
+  if (!staged.alloc_zeros((size_t)K * meta_bytes)) return fail("burst staging alloc failed");
+  std::vector<int> host((size_t)K * mo.total_ints);
+  bool split = false;
+  for (int i = 0; i < K; ++i) {
+    const uint32_t t = i == 0 ? first_token : 0u;
+    if (!build_step_meta(1, 1, &t, &kv_id, host.data() + (size_t)i * mo.total_ints, &split)) return false;
+  }
+  cudaStream_t st = ctx.stream;
+  DeviceBuf toks;
+  if (!toks.alloc_zeros((size_t)K * 4)) return fail("burst alloc failed");
+  if (!cu(cudaMemcpyAsync(staged.ptr, host.data(), (size_t)K * meta_bytes, cudaMemcpyHostToDevice, st), "stage H2D"))
+    return false;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (!cu(cudaStreamSynchronize(st), "burst pre-sync")) return false;
+  cudaEventRecord(e0, st);
+  bool ok = true;
+  for (int i = 0; ok && i < K; ++i) {
+    ok = cu(cudaMemcpyAsync(meta_d.ptr, static_cast<char*>(staged.ptr) + (size_t)i * meta_bytes, meta_bytes,
+                            cudaMemcpyDeviceToDevice, st), "meta D2D");
+    if (ok && i > 0)  // feed the previous arg-max back as this step's token id
+      ok = cu(cudaMemcpyAsync(meta_d.i32() + mo.token_ids, sample_out.ptr, 4, cudaMemcpyDeviceToDevice, st), "tok D2D");
+    ok = ok && run_step_kernels(1, false);
+    ok = ok && cu(cudaMemcpyAsync(toks.i32() + i, sample_out.ptr, 4, cudaMemcpyDeviceToDevice, st), "tok save");
+  }
+  cudaEventRecord(e1, st);
+  ok = ok && cu(cudaStreamSynchronize(st), "burst sync");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_total) *ms_total = ms;
+  if (ok && tokens_out) ok = cu(cudaMemcpy(tokens_out, toks.ptr, (size_t)K * 4, cudaMemcpyDeviceToHost), "tok D2H");
+  return ok;
+}
+
+// The GEMV launches of one fused decode token (36 x {qkv, o, gate_up, down} + lm_head) back to back,
+// `iters` times, timed with CUDA events: the roofline leg of bench.py (weights >> L2, so every pass is
+// cold).  Returns ms per pass and the number of GEMV launches per pass.
+bool Qwen3Model::bench_gemv_pass(int iters, float* ms_per_pass, int* launches_per_pass) {
+  if (!finalized || rt.mode != 1 || tp.is_sharded()) return fail("bench_gemv_pass needs the fused single-GPU path");
+  const Config& c = config;
+  const int H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim(), I = local_inter();
+  cudaStream_t st = ctx.stream;
+  auto gemv = [&](const pk_bf16* W, const pk_bf16* X, int M, int K, pk_bf16* y, int xm, const pk_bf16* res,
+                  const pk_bf16* nw, pk_bf16* hout, int epi) {
+    pk_b200_gemv_args g{};
+    g.W = W; g.X = X; g.Y[0] = y; g.seg_rows[0] = M; g.M = M; g.N = 1; g.K = K;
+    g.x_mode = xm; g.residual = res; g.norm_w = nw; g.eps = c.rms_norm_eps; g.hidden_out = hout; g.epi = epi;
+    return k.pk_b200_gemv_fused(&g, st) == 0;
+  };
+  int n = 0;
+  auto pass = [&]() {
+    bool ok = true;
+    n = 0;
+    for (int li = 0; ok && li < c.num_hidden_layers; ++li) {
+      TransformerBlock& L = layers[li];
+      ok = gemv(L.attention.qkv_proj.data.bf(), hidden.data.bf(), qd + 2 * kd, H, q.data.bf(), 1, zero_residual.bf(),
+                L.input_layernorm.data.bf(), hidden_b.data.bf(), 0) &&
+           gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), 0, nullptr, nullptr, nullptr, 0) &&
+           gemv(L.mlp.gate_up_proj.data.bf(), hidden_b.data.bf(), I, H, mlp_act.data.bf(), 1, zero_residual.bf(),
+                L.post_attention_layernorm.data.bf(), hidden.data.bf(), 1) &&
+           gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), 0, nullptr, nullptr, nullptr, 0);
+      n += 4;
+    }
+    ok = ok && gemv(output_projection().data.bf(), hidden.data.bf(), c.vocab_size, H, logits.data.bf(), 1,
+                    zero_residual.bf(), norm.data.bf(), hidden_b.data.bf(), 0);
+    n += 1;
+    return ok;
+  };
+  if (!pass()) return fail("gemv pass failed");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaStreamSynchronize(st);
+  cudaEventRecord(e0, st);
+  bool ok = true;
+  for (int i = 0; ok && i < iters; ++i) ok = pass();
+  cudaEventRecord(e1, st);
+  ok = ok && cu(cudaStreamSynchronize(st), "gemv pass sync");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_pass = ms / (float)iters;
+  *launches_per_pass = n;
+  return ok;
 }
 
 bool Qwen3Model::sample_greedy(const pk_bf16* lg, int* out) {
@@ -951,6 +1065,31 @@ __attribute__((visibility("default"))) void* pq_debug_buffer(void* mp, const cha
   if (n == "kv") return m->kv_buffer.ptr;
   if (n == "attn_out") return m->attn_out.data.ptr;
   return nullptr;
+}
+
+__attribute__((visibility("default"))) int pq_decode_burst(void* mp, int kv_id, uint32_t first_token, int K,
+                                                           uint32_t* tokens_out, float* ms_total) {
+  return PQ_M->decode_burst(kv_id, first_token, K, tokens_out, ms_total) ? 0 : -1;
+}
+__attribute__((visibility("default"))) int pq_bench_gemv_pass(void* mp, int iters, float* ms_per_pass, int* n) {
+  return PQ_M->bench_gemv_pass(iters, ms_per_pass, n) ? 0 : -1;
+}
+__attribute__((visibility("default"))) int64_t pq_launches_per_step(void* mp) { return PQ_M->launches_per_step; }
+__attribute__((visibility("default"))) int64_t pq_meta_bytes(void* mp) { return (int64_t)PQ_M->meta_bytes; }
+// record a CUDA event pair around caller-driven work on the model's stream (bench.py e2e leg)
+__attribute__((visibility("default"))) void* pq_event_record(void* mp) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  cudaEventRecord(e, PQ_M->ctx.stream);
+  return e;
+}
+__attribute__((visibility("default"))) float pq_event_elapsed_ms(void* e0, void* e1) {
+  float ms = -1.f;
+  cudaEventSynchronize(static_cast<cudaEvent_t>(e1));
+  cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(e0), static_cast<cudaEvent_t>(e1));
+  cudaEventDestroy(static_cast<cudaEvent_t>(e0));
+  cudaEventDestroy(static_cast<cudaEvent_t>(e1));
+  return ms;
 }
 
 // Greedy generation of one request, host token ids in -> host token ids out, timed like

@@ -66,6 +66,16 @@ def host_lib() -> C.CDLL:
         h.pq_debug_buffer.restype = vp
         h.pq_debug_buffer.argtypes = [vp, C.c_char_p]
         h.pq_generate.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        h.pq_decode_burst.argtypes = [vp, i32, C.c_uint32, i32, vp, vp]
+        h.pq_bench_gemv_pass.argtypes = [vp, i32, vp, vp]
+        h.pq_launches_per_step.restype = C.c_int64
+        h.pq_launches_per_step.argtypes = [vp]
+        h.pq_meta_bytes.restype = C.c_int64
+        h.pq_meta_bytes.argtypes = [vp]
+        h.pq_event_record.restype = vp
+        h.pq_event_record.argtypes = [vp]
+        h.pq_event_elapsed_ms.restype = C.c_float
+        h.pq_event_elapsed_ms.argtypes = [vp, vp]
         _host = h
     return _host
 
@@ -84,8 +94,10 @@ class ModelRuntimeConfig:
 
 
 class Qwen3Model:
-    def __init__(self, cfg: Qwen3Config, weights: dict[str, torch.Tensor],
+    def __init__(self, cfg: Qwen3Config, weights,
                  runtime: ModelRuntimeConfig | None = None, tp_comm: int | None = None):
+        """``weights``: dict or iterable of (HF tensor name, bf16 tensor on host or device); every
+        tensor is the FULL unsharded matrix, the loader takes this rank's shard (weights.rs:121-291)."""
         rt = runtime or ModelRuntimeConfig()
         rt.tensor_parallel.validate_for(cfg)
         if not torch.cuda.is_available():
@@ -103,9 +115,11 @@ class Qwen3Model:
         self._m = self._h.pq_model_create(C.byref(pc), C.byref(pr), lib_path.encode(), tp_comm)
         if not self._m:
             raise RuntimeError("pq_model_create: " + self._h.pq_create_error().decode())
-        for name, t in weights.items():
+        for name, t in (weights.items() if isinstance(weights, dict) else weights):
             if name == "lm_head.weight" and cfg.tie_word_embeddings:
                 continue
+            if t.is_cuda:
+                torch.cuda.current_stream().synchronize()
             assert t.dtype == torch.bfloat16 and t.is_contiguous(), name
             rows, cols = (t.shape[0], t.shape[1]) if t.dim() == 2 else (1, t.shape[0])
             self._ck(self._h.pq_model_load_tensor(self._m, name.encode(), t.data_ptr(), rows, cols))
@@ -176,6 +190,30 @@ class Qwen3Model:
         steps = (C.c_double * max(1, max_tokens - 1))()
         self._ck(self._h.pq_generate(self._m, toks, len(prompt), max_tokens, out, C.byref(ttft), steps))
         return list(out), ttft.value, list(steps)[:max_tokens - 1]
+
+    def decode_burst(self, kv_id: int, first_token: int, steps: int):
+        """`steps` greedy decode steps with no host round trip (bench.py's device-resident leg)."""
+        out = (C.c_uint32 * steps)()
+        ms = C.c_float()
+        self._ck(self._h.pq_decode_burst(self._m, kv_id, first_token, steps, out, C.byref(ms)))
+        return list(out), ms.value
+
+    def bench_gemv_pass(self, iters: int):
+        ms, n = C.c_float(), C.c_int()
+        self._ck(self._h.pq_bench_gemv_pass(self._m, iters, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launches_per_step(self) -> int:
+        return int(self._h.pq_launches_per_step(self._m))
+
+    def meta_bytes(self) -> int:
+        return int(self._h.pq_meta_bytes(self._m))
+
+    def event_record(self):
+        return self._h.pq_event_record(self._m)
+
+    def event_elapsed_ms(self, e0, e1) -> float:
+        return float(self._h.pq_event_elapsed_ms(e0, e1))
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self._h.pq_launch_count(self._m, int(reset)))

@@ -38,25 +38,35 @@ def weight_shapes(cfg: Qwen3Config) -> dict[str, tuple[int, ...]]:
     return s
 
 
-def random_weights(cfg: Qwen3Config, seed: int = 0, device: str = "cpu",
-                   norm_jitter: float = 0.0) -> dict[str, torch.Tensor]:
-    """bf16 tensors by HF name.  Deterministic per (seed, device type, tensor order).
+def iter_random_weights(cfg: Qwen3Config, seed: int = 0, device: str = "cpu", norm_jitter: float = 0.0):
+    """Yield (HF name, bf16 tensor) one at a time (a 4B/8B checkpoint never sits in memory twice).
+    Deterministic per (seed, device type, tensor order).
 
-    ``norm_jitter`` > 0 perturbs norm weights away from 1.0 (tests only) so a
-    dropped weight multiply cannot hide.
+    ``norm_jitter`` > 0 perturbs norm weights away from 1.0 (tests only) so a dropped weight
+    multiply cannot hide.
     """
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    out: dict[str, torch.Tensor] = {}
     for name, shape in weight_shapes(cfg).items():
         if len(shape) == 1:
             t = torch.ones(shape, dtype=torch.float32, device=device)
             if norm_jitter:
                 t += norm_jitter * torch.randn(shape, generator=g, dtype=torch.float32, device=device)
+            yield name, t.to(torch.bfloat16)
         else:
-            t = torch.randn(shape, generator=g, dtype=torch.float32, device=device) * 0.02
-        out[name] = t.to(torch.bfloat16)
-    return out
+            t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            rows = max(1, (1 << 26) // shape[1])  # fp32 staging in <= 256 MB pieces
+            for r0 in range(0, shape[0], rows):
+                r1 = min(shape[0], r0 + rows)
+                t[r0:r1] = (torch.randn((r1 - r0, shape[1]), generator=g, dtype=torch.float32, device=device)
+                            * 0.02).to(torch.bfloat16)
+            yield name, t
+
+
+def random_weights(cfg: Qwen3Config, seed: int = 0, device: str = "cpu",
+                   norm_jitter: float = 0.0) -> dict[str, torch.Tensor]:
+    """bf16 tensors by HF name (see iter_random_weights)."""
+    return dict(iter_random_weights(cfg, seed, device, norm_jitter))
 
 
 def to_numpy_bits(weights: dict[str, torch.Tensor]):
