@@ -190,7 +190,10 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   const int new_pos = inject_new ? a.positions[b] : -1;
   const bf16* kbase = a.kv + a.k_off + (int64_t)kvh * HD + l16 * 8;
   const bf16* vbase = a.kv + a.v_off + (int64_t)kvh * HD + l16 * 8;
-  for (int base = lo + warp * 2 + half; base < hi; base += kTokPerStep * kUnroll) {
+  // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): iterate on the warp's
+  // base token and let each half-warp mask its own token.
+  for (int base0 = lo + warp * 2; base0 < hi; base0 += kTokPerStep * kUnroll) {
+    const int base = base0 + half;
     uint4 kr[kUnroll], vr[kUnroll];
     bool ok[kUnroll];
 #pragma unroll
@@ -226,7 +229,11 @@ decode_attention_kernel(const DecodeAttnArgs a) {
       float mn = m[h];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) mn = fmaxf(mn, s[h][u]);
-      if (mn == -INFINITY) continue;  // nothing valid yet
+      if (mn == -INFINITY) {  // nothing valid yet: p = 0 (never let -inf reach the PV FMAs)
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) s[h][u] = 0.f;
+        continue;
+      }
       const float sc = ex2(m[h] - mn);  // m = -inf -> 0
       m[h] = mn;
       d[h] *= sc;

