@@ -197,6 +197,10 @@ typedef struct {
   int epi;
 } pk_b200_gemv_args;
 int pk_b200_gemv_fused(const pk_b200_gemv_args* args, pk_stream stream);
+/* Ring depth (2..12 stages of 8 row segments), CTAs per SM and K elements per row segment (multiple of
+ * 256) of the streaming GEMV; 0 keeps a value.  Defaults: PK_GEMV_STAGES / PK_GEMV_CTAS_PER_SM /
+ * PK_GEMV_KC or the built-in tuning. */
+void pk_b200_set_gemv_tuning(int stages, int ctas_per_sm, int segment_elems);
 
 /* QK-norm + RoPE + KV append + split-KV GQA decode attention + merge in ONE launch.
  * q/k/v are the raw projections of the step ([dim, bs]); k is normed/roped and both k, v

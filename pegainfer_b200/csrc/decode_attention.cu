@@ -23,7 +23,7 @@ constexpr int HD = 128;
 constexpr int kAttWarps = 4;
 constexpr int kAttThreads = kAttWarps * 32;
 constexpr int kTokPerStep = kAttWarps * 2;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;   // 64 tokens (4 pages) per CTA round; all K/V rows of a round in flight
 constexpr int kPartStride = HD + 2;  // o[128], m, d
 
 struct DecodeAttnArgs {
@@ -190,10 +190,14 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   const int new_pos = inject_new ? a.positions[b] : -1;
   const bf16* kbase = a.kv + a.k_off + (int64_t)kvh * HD + l16 * 8;
   const bf16* vbase = a.kv + a.v_off + (int64_t)kvh * HD + l16 * 8;
-  // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): iterate on the warp's
-  // base token and let each half-warp mask its own token.
-  for (int base0 = lo + warp * 2; base0 < hi; base0 += kTokPerStep * kUnroll) {
-    const int base = base0 + half;
+  // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): iterate on the CTA's round
+  // base and let each half-warp mask its own tokens.  A round is 64 tokens = 4 pages: the 4 page ids
+  // are fetched first (one latency), then all 8 K and 8 V rows of the half-warp (one latency).
+  for (int round = lo; round < hi; round += kTokPerStep * kUnroll) {
+    const int base = round + warp * 2 + half;
+    int pg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pg[i] = (round + 16 * i < hi) ? __ldg(pages + (round >> 4) + i) : 0;
     uint4 kr[kUnroll], vr[kUnroll];
     bool ok[kUnroll];
 #pragma unroll
@@ -203,7 +207,9 @@ decode_attention_kernel(const DecodeAttnArgs a) {
       kr[u] = make_uint4(0, 0, 0, 0);
       vr[u] = make_uint4(0, 0, 0, 0);
       if (ok[u]) {
-        const int page = __ldg(pages + t / a.page_size), slot = t % a.page_size;
+        // (t - round) / 16 == u / 2 because warp*2+half < 8; page_size is 16 on this path
+        const int page = a.page_size == 16 ? pg[u >> 1] : __ldg(pages + t / a.page_size);
+        const int slot = t % a.page_size;
         const int64_t off = (int64_t)page * a.stride_page + (int64_t)slot * a.nkv * HD;
         kr[u] = ldg_stream(kbase + off);
         vr[u] = ldg_stream(vbase + off);
@@ -340,20 +346,45 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-#pragma unroll
-  for (int h = 0; h < GROUP; ++h) {
+  // ---- last CTA: weights of all chunks first (warp-parallel over chunks), then one unrolled pass ----
+  float* sw = &st_o[0][0][0];  // reuse: [nchunks][GROUP] weights, then [GROUP] denominators
+  float* sD = sw + 64 * GROUP;
+  __syncthreads();
+  for (int h = warp; h < GROUP; h += kAttWarps) {
     const float* p0 =
         a.partial + (((size_t)out_slot * a.max_chunks) * a.nq + kvh * GROUP + h) * kPartStride;
     const size_t cstride = (size_t)a.nq * kPartStride;
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) mx = fmaxf(mx, __ldcg(p0 + c * cstride + HD));
-    float dd = 0.f, oo = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const float w = ex2(__ldcg(p0 + c * cstride + HD) - mx);
-      dd = fmaf(__ldcg(p0 + c * cstride + HD + 1), w, dd);
-      oo = fmaf(__ldcg(p0 + c * cstride + t), w, oo);
+    const int c0 = lane, c1 = lane + 32;
+    const float m0 = c0 < nchunks ? __ldcg(p0 + c0 * cstride + HD) : -INFINITY;
+    const float m1 = c1 < nchunks ? __ldcg(p0 + c1 * cstride + HD) : -INFINITY;
+    const float d0 = c0 < nchunks ? __ldcg(p0 + c0 * cstride + HD + 1) : 0.f;
+    const float d1 = c1 < nchunks ? __ldcg(p0 + c1 * cstride + HD + 1) : 0.f;
+    const float mx = warp_max(fmaxf(m0, m1));
+    const float w0 = ex2(m0 - mx), w1 = ex2(m1 - mx);
+    sw[c0 * GROUP + h] = w0;
+    sw[c1 * GROUP + h] = w1;
+    const float dd = warp_sum(d0 * w0 + d1 * w1);
+    if (lane == 0) sD[h] = dd;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < GROUP; ++h) {
+    const float* p0 =
+        a.partial + (((size_t)out_slot * a.max_chunks) * a.nq + kvh * GROUP + h) * kPartStride + t;
+    const size_t cstride = (size_t)a.nq * kPartStride;
+    float oo0 = 0.f, oo1 = 0.f, oo2 = 0.f, oo3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= nchunks; c += 4) {
+      const float v0 = __ldcg(p0 + (c + 0) * cstride), v1 = __ldcg(p0 + (c + 1) * cstride);
+      const float v2 = __ldcg(p0 + (c + 2) * cstride), v3 = __ldcg(p0 + (c + 3) * cstride);
+      oo0 = fmaf(v0, sw[(c + 0) * GROUP + h], oo0);
+      oo1 = fmaf(v1, sw[(c + 1) * GROUP + h], oo1);
+      oo2 = fmaf(v2, sw[(c + 2) * GROUP + h], oo2);
+      oo3 = fmaf(v3, sw[(c + 3) * GROUP + h], oo3);
     }
-    a.out[((size_t)out_slot * a.nq + kvh * GROUP + h) * HD + t] = f2bf(__fdividef(oo, dd));
+    for (; c < nchunks; ++c) oo0 = fmaf(__ldcg(p0 + c * cstride), sw[c * GROUP + h], oo0);
+    a.out[((size_t)out_slot * a.nq + kvh * GROUP + h) * HD + t] =
+        f2bf(__fdividef((oo0 + oo1) + (oo2 + oo3), sD[h]));
   }
   if (t == 0) a.counters[out_slot * a.nkv + kvh] = 0;  // graph-replayable
 }

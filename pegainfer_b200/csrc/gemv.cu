@@ -23,9 +23,6 @@
 namespace pk {
 
 constexpr int kCW = 8;            // consumer warps (rows per group)
-constexpr int kKC = 1024;         // K elements per row segment per stage (2 KB)
-constexpr int kSegBytes = kKC * 2;
-constexpr int kStageBytes = kCW * kSegBytes;  // 16 KB
 constexpr int kMaxStages = 12;
 constexpr int kConsumerThreads = kCW * 32;
 
@@ -43,18 +40,21 @@ struct GemvArgs {
   bf16* normed_out;
   int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows)
   int stages;
+  int kc;       // K elements per row segment per stage (multiple of 256); stage = 8 segments
 };
 
+// 8 bf16 x bf16 products onto `acc`, as two interleaved 4-long FMA chains (ILP: the consumer loop is
+// latency-bound on dependent FMAs otherwise -- profiles/r1_gemv_v1.md)
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
-  acc = fmaf(bf16_lo(w.x), bf16_lo(x.x), acc);
-  acc = fmaf(bf16_hi(w.x), bf16_hi(x.x), acc);
-  acc = fmaf(bf16_lo(w.y), bf16_lo(x.y), acc);
-  acc = fmaf(bf16_hi(w.y), bf16_hi(x.y), acc);
-  acc = fmaf(bf16_lo(w.z), bf16_lo(x.z), acc);
-  acc = fmaf(bf16_hi(w.z), bf16_hi(x.z), acc);
-  acc = fmaf(bf16_lo(w.w), bf16_lo(x.w), acc);
-  acc = fmaf(bf16_hi(w.w), bf16_hi(x.w), acc);
-  return acc;
+  float a = fmaf(bf16_lo(w.x), bf16_lo(x.x), acc);
+  float b = bf16_hi(w.x) * bf16_hi(x.x);
+  a = fmaf(bf16_lo(w.y), bf16_lo(x.y), a);
+  b = fmaf(bf16_hi(w.y), bf16_hi(x.y), b);
+  a = fmaf(bf16_lo(w.z), bf16_lo(x.z), a);
+  b = fmaf(bf16_hi(w.z), bf16_hi(x.z), b);
+  a = fmaf(bf16_lo(w.w), bf16_lo(x.w), a);
+  b = fmaf(bf16_hi(w.w), bf16_hi(x.w), b);
+  return a + b;
 }
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(kConsumerThreads + 32, 1)
 gemv_stream_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int stages = a.stages;
+  const int kKC = a.kc;
+  const int kSegBytes = kKC * 2, kStageBytes = kCW * kSegBytes;
   uint8_t* ring = smem;
   bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)stages * kStageBytes);  // [NTOK][K]
   const size_t x_bytes = (((size_t)NTOK * a.K * 2) + 15) & ~(size_t)15;
@@ -93,7 +95,8 @@ gemv_stream_kernel(const GemvArgs a) {
   if (warp == kCW) {
     // ===== producer warp: lanes 0..7 each stream one row segment per stage =====
     const uint64_t pol = l2_evict_first_policy();
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int g = 0; g < groups; ++g) {
       // source row of consumer slot `lane` in this group (-1: none)
       int src = -1;
@@ -103,9 +106,7 @@ gemv_stream_kernel(const GemvArgs a) {
       }
       const unsigned valid = __ballot_sync(0xffffffffu, src >= 0);
       const int nvalid = __popc(valid);
-      for (int c = 0; c < chunks; ++c, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)((it / stages) & 1);
+      for (int c = 0; c < chunks; ++c) {
         const int k0 = c * kKC;
         const uint32_t bytes = (uint32_t)(min(kKC, K - k0) * 2);
         if (lane == 0) {
@@ -116,6 +117,10 @@ gemv_stream_kernel(const GemvArgs a) {
         if (src >= 0)
           bulk_g2s(ring + (size_t)s * kStageBytes + (size_t)lane * kSegBytes,
                    a.W + (size_t)src * K + k0, bytes, full + s, pol);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     return;
@@ -130,20 +135,27 @@ gemv_stream_kernel(const GemvArgs a) {
       for (int i = tid; i < nv; i += kConsumerThreads)
         reinterpret_cast<uint4*>(xs)[i] = reinterpret_cast<const uint4*>(a.X)[i];
     } else {
-      // x = bf16((h + r) * rsqrt(mean((h+r)^2) + eps) * w); hidden_out = bf16(h + r)
+      // x = bf16((h + r) * rsqrt(mean((h+r)^2) + eps) * w); hidden_out = bf16(h + r).
+      // One pass over global memory: each thread keeps its <= 5 vectors of the row in registers.
+      constexpr int kMaxVec = 5;  // K <= 5 * 256 * 8 = 10240
       const int nv = K >> 3;
       for (int n = 0; n < NTOK; ++n) {
         const uint4* h4 = reinterpret_cast<const uint4*>(a.X + (size_t)n * K);
         const uint4* r4 = reinterpret_cast<const uint4*>(a.residual + (size_t)n * K);
+        float v[kMaxVec][8];
         float ss = 0.f;
-        for (int i = tid; i < nv; i += kConsumerThreads) {
-          const uint4 h = h4[i], r = r4[i];
-          const float v[8] = {bf16_lo(h.x) + bf16_lo(r.x), bf16_hi(h.x) + bf16_hi(r.x),
-                              bf16_lo(h.y) + bf16_lo(r.y), bf16_hi(h.y) + bf16_hi(r.y),
-                              bf16_lo(h.z) + bf16_lo(r.z), bf16_hi(h.z) + bf16_hi(r.z),
-                              bf16_lo(h.w) + bf16_lo(r.w), bf16_hi(h.w) + bf16_hi(r.w)};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+        for (int j = 0; j < kMaxVec; ++j) {
+          const int i = tid + j * kConsumerThreads;
+          if (i < nv) {
+            const uint4 h = h4[i], r = r4[i];
+            v[j][0] = bf16_lo(h.x) + bf16_lo(r.x); v[j][1] = bf16_hi(h.x) + bf16_hi(r.x);
+            v[j][2] = bf16_lo(h.y) + bf16_lo(r.y); v[j][3] = bf16_hi(h.y) + bf16_hi(r.y);
+            v[j][4] = bf16_lo(h.z) + bf16_lo(r.z); v[j][5] = bf16_hi(h.z) + bf16_hi(r.z);
+            v[j][6] = bf16_lo(h.w) + bf16_lo(r.w); v[j][7] = bf16_hi(h.w) + bf16_hi(r.w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
+          }
         }
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
@@ -154,26 +166,26 @@ gemv_stream_kernel(const GemvArgs a) {
         consumer_bar();
         const float rinv = rsqrtf(tot / (float)K + a.eps);
         const uint4* g4 = reinterpret_cast<const uint4*>(a.norm_w);
-        for (int i = tid; i < nv; i += kConsumerThreads) {
-          const uint4 h = h4[i], r = r4[i], g = g4[i];
-          const float v[8] = {bf16_lo(h.x) + bf16_lo(r.x), bf16_hi(h.x) + bf16_hi(r.x),
-                              bf16_lo(h.y) + bf16_lo(r.y), bf16_hi(h.y) + bf16_hi(r.y),
-                              bf16_lo(h.z) + bf16_lo(r.z), bf16_hi(h.z) + bf16_hi(r.z),
-                              bf16_lo(h.w) + bf16_lo(r.w), bf16_hi(h.w) + bf16_hi(r.w)};
-          uint4 o;
-          o.x = pack_bf16(v[0] * rinv * bf16_lo(g.x), v[1] * rinv * bf16_hi(g.x));
-          o.y = pack_bf16(v[2] * rinv * bf16_lo(g.y), v[3] * rinv * bf16_hi(g.y));
-          o.z = pack_bf16(v[4] * rinv * bf16_lo(g.z), v[5] * rinv * bf16_hi(g.z));
-          o.w = pack_bf16(v[6] * rinv * bf16_lo(g.w), v[7] * rinv * bf16_hi(g.w));
-          reinterpret_cast<uint4*>(xs + (size_t)n * K)[i] = o;
-          if (blockIdx.x == 0) {
-            uint4 hs;
-            hs.x = pack_bf16(v[0], v[1]);
-            hs.y = pack_bf16(v[2], v[3]);
-            hs.z = pack_bf16(v[4], v[5]);
-            hs.w = pack_bf16(v[6], v[7]);
-            reinterpret_cast<uint4*>(a.hidden_out + (size_t)n * K)[i] = hs;
-            if (a.normed_out) reinterpret_cast<uint4*>(a.normed_out + (size_t)n * K)[i] = o;
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+          const int i = tid + j * kConsumerThreads;
+          if (i < nv) {
+            const uint4 g = g4[i];
+            uint4 o;
+            o.x = pack_bf16(v[j][0] * rinv * bf16_lo(g.x), v[j][1] * rinv * bf16_hi(g.x));
+            o.y = pack_bf16(v[j][2] * rinv * bf16_lo(g.y), v[j][3] * rinv * bf16_hi(g.y));
+            o.z = pack_bf16(v[j][4] * rinv * bf16_lo(g.z), v[j][5] * rinv * bf16_hi(g.z));
+            o.w = pack_bf16(v[j][6] * rinv * bf16_lo(g.w), v[j][7] * rinv * bf16_hi(g.w));
+            reinterpret_cast<uint4*>(xs + (size_t)n * K)[i] = o;
+            if (blockIdx.x == 0) {
+              uint4 hs;
+              hs.x = pack_bf16(v[j][0], v[j][1]);
+              hs.y = pack_bf16(v[j][2], v[j][3]);
+              hs.z = pack_bf16(v[j][4], v[j][5]);
+              hs.w = pack_bf16(v[j][6], v[j][7]);
+              reinterpret_cast<uint4*>(a.hidden_out + (size_t)n * K)[i] = hs;
+              if (a.normed_out) reinterpret_cast<uint4*>(a.normed_out + (size_t)n * K)[i] = o;
+            }
           }
         }
       }
@@ -181,35 +193,57 @@ gemv_stream_kernel(const GemvArgs a) {
     consumer_bar();
   }
 
-  int it = 0;
+  int s = 0;
+  uint32_t ph = 0;
   for (int g = 0; g < groups; ++g) {
     const int out_row = r0 + g * rows_per_group + (a.epi == 1 ? (warp & 3) : warp);
     const bool has_row = out_row < r1;
-    float acc[NTOK];
+    float acc4[NTOK][4];
 #pragma unroll
-    for (int n = 0; n < NTOK; ++n) acc[n] = 0.f;
-    for (int c = 0; c < chunks; ++c, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)((it / stages) & 1);
+    for (int n = 0; n < NTOK; ++n) acc4[n][0] = acc4[n][1] = acc4[n][2] = acc4[n][3] = 0.f;
+    for (int c = 0; c < chunks; ++c) {
       mbar_wait(full + s, ph);
       if (has_row) {
         const int k0 = c * kKC;
         const int nvec = min(kKC, K - k0) >> 3;
         const uint4* wseg =
             reinterpret_cast<const uint4*>(ring + (size_t)s * kStageBytes + (size_t)warp * kSegBytes);
-#pragma unroll 4
-        for (int i = lane; i < nvec; i += 32) {
+        int v0 = 0;
+        for (; v0 + 128 <= nvec; v0 += 128) {
+          // 2 KB of the segment: 4 vectors per lane, all shared-memory loads issued before the FMAs,
+          // four independent accumulators per token
+          uint4 wv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wv[i] = wseg[v0 + lane + 32 * i];
+#pragma unroll
+          for (int n = 0; n < NTOK; ++n) {
+            const uint4* xp = reinterpret_cast<const uint4*>(xs + (size_t)n * K + k0) + v0;
+            uint4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xp[lane + 32 * i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc4[n][i] = dot8(wv[i], xv[i], acc4[n][i]);
+          }
+        }
+        for (int i = v0 + lane; i < nvec; i += 32) {
           const uint4 wv = wseg[i];
 #pragma unroll
           for (int n = 0; n < NTOK; ++n) {
             const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)n * K + k0)[i];
-            acc[n] = dot8(wv, xv, acc[n]);
+            acc4[n][0] = dot8(wv, xv, acc4[n][0]);
           }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
+    float acc[NTOK];
+#pragma unroll
+    for (int n = 0; n < NTOK; ++n) acc[n] = (acc4[n][0] + acc4[n][1]) + (acc4[n][2] + acc4[n][3]);
 #pragma unroll
     for (int n = 0; n < NTOK; ++n) acc[n] = warp_sum(acc[n]);
     if (a.epi == 0) {
@@ -257,21 +291,31 @@ __global__ void gemv_generic_kernel(const bf16* __restrict__ W, const bf16* __re
   }
 }
 
-static int g_gemv_stages = 0, g_gemv_ctas_per_sm = 0;
+static int g_gemv_stages = 0, g_gemv_ctas_per_sm = 0, g_gemv_kc = 0;
 
 static void gemv_tuning() {
   if (g_gemv_stages == 0) {
     const char* s = getenv("PK_GEMV_STAGES");
-    g_gemv_stages = s ? atoi(s) : 6;
+    g_gemv_stages = s ? atoi(s) : 4;
     if (g_gemv_stages < 2) g_gemv_stages = 2;
     if (g_gemv_stages > kMaxStages) g_gemv_stages = kMaxStages;
     const char* c = getenv("PK_GEMV_CTAS_PER_SM");
-    g_gemv_ctas_per_sm = c ? atoi(c) : 1;
+    g_gemv_ctas_per_sm = c ? atoi(c) : 2;
     if (g_gemv_ctas_per_sm < 1) g_gemv_ctas_per_sm = 1;
+    const char* k = getenv("PK_GEMV_KC");
+    g_gemv_kc = k ? atoi(k) : 1024;
+    if (g_gemv_kc < 256 || g_gemv_kc % 256) g_gemv_kc = 1024;
   }
 }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void gemv_set_tuning(int stages, int ctas_per_sm, int kc) {
+  gemv_tuning();
+  if (stages >= 2 && stages <= kMaxStages) g_gemv_stages = stages;
+  if (ctas_per_sm >= 1 && ctas_per_sm <= 4) g_gemv_ctas_per_sm = ctas_per_sm;
+  if (kc >= 256 && kc % 256 == 0 && kc <= 16384) g_gemv_kc = kc;
+}
 
 bool gemv_stream_supported(const void* W, const void* X, int N, int K) {
   return N >= 1 && N <= 4 && K % 8 == 0 && al16(W) && al16(X) && (size_t)N * K * 2 <= 96 * 1024;
@@ -281,11 +325,16 @@ template <int NTOK>
 static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
   gemv_tuning();
   int stages = g_gemv_stages;
+  int kc = g_gemv_kc;
+  while (kc > 256 && kc / 2 >= a.K) kc /= 2;  // no point in segments longer than a row
   const size_t x_bytes = (((size_t)NTOK * a.K * 2) + 15) & ~(size_t)15;
   const size_t tail = 2 * kMaxStages * sizeof(uint64_t) + 64 * sizeof(float);
-  while (stages > 2 && (size_t)stages * kStageBytes + x_bytes + tail > 200 * 1024) --stages;
+  const size_t budget = (g_gemv_ctas_per_sm >= 2 ? 112 : 224) * 1024;
+  while (stages > 2 && (size_t)stages * kCW * kc * 2 + x_bytes + tail > budget) --stages;
+  while (kc > 256 && (size_t)stages * kCW * kc * 2 + x_bytes + tail > budget) kc -= 256;
   a.stages = stages;
-  const size_t smem = (size_t)stages * kStageBytes + x_bytes + tail;
+  a.kc = kc;
+  const size_t smem = (size_t)stages * kCW * kc * 2 + x_bytes + tail;
   auto kern = gemv_stream_kernel<NTOK>;
   static thread_local size_t configured[5] = {0, 0, 0, 0, 0};
   if (smem > configured[NTOK]) {
@@ -351,11 +400,16 @@ void gemm_graphsafe_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, 
   launch_gemv(a, N, stream);
 }
 
+// ring depth (2..12 stages), CTAs per SM and K elements per row segment of the streaming GEMV; 0 keeps a value
+void pk_b200_set_gemv_tuning(int stages, int ctas_per_sm, int segment_elems) {
+  pk::gemv_set_tuning(stages, ctas_per_sm, segment_elems);
+}
+
 int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
   using namespace pk;
   if (!g || g->M <= 0 || g->K <= 0) return -1;
   if (!gemv_stream_supported(g->W, g->X, g->N, g->K)) return -1;
-  if (g->x_mode == 1 && (g->hidden_out == nullptr || g->hidden_out == g->X)) return -1;
+  if (g->x_mode == 1 && (g->hidden_out == nullptr || g->hidden_out == g->X || g->K > 10240)) return -1;
   GemvArgs a{};
   a.W = (const bf16*)g->W;
   a.X = (const bf16*)g->X;
