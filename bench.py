@@ -211,8 +211,10 @@ def run_ours(args, cfg, rank, world, dist):
         raise SystemExit(f"prompt {prompt_len} + steps exceed the reference's 4096-position RoPE table")
     pages = 3 * (ctx_max // 16 + 2) + 8
     tp_comm = make_tp_comm(rank, world, dist, max_tokens=256, hidden=cfg.hidden_size) if world > 1 else None
+    persistent = world == 1 and os.environ.get("PK_DECODE", "persistent") == "persistent"
     rt = ModelRuntimeConfig(enable_cuda_graph=True, tensor_parallel=TensorParallelConfig(rank, world),
-                            device_ordinal=local_rank, fused=True, num_pages=pages, max_batch=1, enable_pdl=True)
+                            device_ordinal=local_rank, fused=True, persistent=persistent, num_pages=pages,
+                            max_batch=1, enable_pdl=True)
     t0 = time.perf_counter()
     model = Qwen3Model(cfg, iter_random_weights(cfg, seed=0, device="cuda"), rt, tp_comm=tp_comm)
     load_s = time.perf_counter() - t0
@@ -292,6 +294,7 @@ def run_ours(args, cfg, rank, world, dist):
                 "config": {"workload": bench_workload_name(cfg, world), "prompt_len": prompt_len,
                            "decode_ctx": [ctx_lo, ctx_lo + K], "l2": "inputs (weights 8-15 GB/token) >> 126 MB L2, no flush needed",
                            "parallelism": f"tp{world}", "cuda_graph": True, "pdl": True,
+                           "decode_impl": "persistent single-launch step" if persistent else "fused multi-kernel graph",
                            "launches_per_step": launches_per_step, "model_load_s": round(load_s, 1)},
                 "ttft_ms": ttft_ms, "ttft_prompt_len": prompt_len,
                 "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "tok/s", "ms_per_step": e2e_ms / K,

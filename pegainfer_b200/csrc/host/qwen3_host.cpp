@@ -32,7 +32,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_REQ(paged_attention_decode_cuda) PQ_REQ(paged_attention_decode_split_kv_cuda)
   PQ_REQ(flashinfer_top1_cuda)
   PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused)
-  PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_tp_all_reduce_rows)
+  PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
 #undef PQ_REQ
 #undef PQ_OPT
@@ -229,6 +229,8 @@ struct Qwen3Model {
   int64_t launches_per_step = 0;
   bool decode_kernels_compat(int bs, bool split);
   bool decode_kernels_fused(int bs);
+  bool decode_kernels_persistent();
+  DeviceBuf layer_ptrs_d, sync_scratch;
   bool ensure_capacity(KvState& s, int tokens);
   bool sample_greedy(const pk_bf16* logits, int* out);
   ~Qwen3Model();
@@ -716,11 +718,54 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
   return true;
 }
 
+// mode 2: the whole token in one cooperative launch (decode_persistent.cu)
+bool Qwen3Model::decode_kernels_persistent() {
+  const Config& c = config;
+  if (!layer_ptrs_d.ptr) {
+    std::vector<pk_b200_layer_ptrs> lp(c.num_hidden_layers);
+    for (int i = 0; i < c.num_hidden_layers; ++i) {
+      TransformerBlock& L = layers[i];
+      lp[i] = pk_b200_layer_ptrs{L.attention.qkv_proj.data.bf(), L.attention.o_proj.data.bf(),
+                                 L.mlp.gate_up_proj.data.bf(), L.mlp.down_proj.data.bf(),
+                                 L.input_layernorm.data.bf(), L.post_attention_layernorm.data.bf(),
+                                 L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf()};
+    }
+    if (!layer_ptrs_d.alloc_zeros(lp.size() * sizeof(pk_b200_layer_ptrs)) || !sync_scratch.alloc_zeros(8192))
+      return fail("persistent decode scratch allocation failed");
+    if (!cu(cudaMemcpy(layer_ptrs_d.ptr, lp.data(), lp.size() * sizeof(pk_b200_layer_ptrs), cudaMemcpyHostToDevice),
+            "layer pointer upload"))
+      return false;
+  }
+  const int* M = meta_d.i32();
+  pk_b200_decode_step_args g{};
+  g.layers_dev = layer_ptrs_d.ptr;
+  g.num_layers = c.num_hidden_layers; g.hidden_size = c.hidden_size; g.intermediate_size = local_inter();
+  g.vocab_size = c.vocab_size; g.num_q_heads = local_heads(); g.num_kv_heads = local_kv_heads();
+  g.head_dim = c.head_dim; g.page_size = kPageSize;
+  g.rms_eps = c.rms_norm_eps; g.sm_scale = 1.0f / sqrtf((float)c.head_dim);
+  g.embed = embed_tokens.data.bf(); g.lm_head = output_projection().data.bf(); g.final_norm = norm.data.bf();
+  g.cos_cache = cos_cache.data.bf(); g.sin_cache = sin_cache.data.bf(); g.zero_residual = zero_residual.bf();
+  g.token_ids = reinterpret_cast<const uint32_t*>(M + mo.token_ids);
+  g.positions = M + mo.positions; g.page_indices = M + mo.page_indices; g.page_indptr = M + mo.page_indptr;
+  g.last_page_len = M + mo.last_page_len;
+  g.kv_data = kv_buffer.bf(); g.layer_stride = layout.layer_stride; g.kv_block_len = layout.kv_block_len;
+  g.stride_page = layout.page_stride;
+  g.hidden_a = hidden.data.bf(); g.hidden_b = hidden_b.data.bf(); g.q = q.data.bf(); g.k = kbuf.data.bf();
+  g.v = v.data.bf(); g.attn_out = attn_out.data.bf(); g.attn_proj = attn_proj.data.bf();
+  g.mlp_act = mlp_act.data.bf(); g.mlp_out = mlp_out.data.bf(); g.logits = logits.data.bf();
+  g.attn_partial = static_cast<float*>(attn_partial.ptr); g.attn_counters = attn_counters.i32();
+  g.attn_max_chunks = attn_max_chunks;
+  g.sync_scratch = sync_scratch.ptr; g.sample_out = sample_out.i32();
+  const int rc = k.pk_b200_decode_step_persistent(&g, ctx.stream);
+  if (rc != 0) return fail("pk_b200_decode_step_persistent failed (rc " + std::to_string(rc) + ")");
+  return true;
+}
+
 // Advance the KV states by one token and write the step's packed metadata block into `mh`
 // (batch_decode.rs:26-59 + sync_paged_meta / sync_split_kv_meta of batch_decode_buffers.rs:177-279).
 bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, const int* kv_ids, int* mh,
                                  bool* split_out) {
-  const bool fused = rt.mode == 1;
+  const bool fused = rt.mode >= 1;
   std::vector<int> positions(bs);
   for (int b = 0; b < bs; ++b) {
     if (kv_ids[b] < 0 || kv_ids[b] >= (int)kv_states.size() || !kv_states[kv_ids[b]].live) return fail("bad kv id");
@@ -779,11 +824,16 @@ bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, con
 
 // CudaGraphState::run_or_capture (cuda_graph.rs:28-58) around the decode body
 bool Qwen3Model::run_step_kernels(int padded, bool split) {
-  const bool fused = rt.mode == 1;
+  const bool fused = rt.mode >= 1;
   cudaStream_t st = ctx.stream;
-  auto body = [&]() { return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split); };
+  const bool persistent = rt.mode == 2 && padded == 1 && !tp.is_sharded() && k.pk_b200_decode_step_persistent &&
+                          local_heads() == 4 * local_kv_heads() && config.hidden_size <= 6144;
+  auto body = [&]() {
+    if (persistent) return decode_kernels_persistent();
+    return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split);
+  };
   if (!rt.enable_cuda_graph) return body();
-  const int key = padded * 4 + (fused ? 2 : (split ? 1 : 0));
+  const int key = padded * 4 + (persistent ? 3 : (fused ? 2 : (split ? 1 : 0)));
   auto& g = graphs[key];
   if (!g) g.reset(new CudaGraphState());
   if (!g->captured()) {
@@ -808,7 +858,7 @@ bool Qwen3Model::run_step_kernels(int padded, bool split) {
 bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void** logits_out, int* sampled) {
   if (!finalized) return fail("model not finalized");
   if (bs <= 0 || bs > max_bs) return fail("batch size out of range");
-  const bool fused = rt.mode == 1;
+  const bool fused = rt.mode >= 1;
   if (fused && bs > 4) return fail("fused decode path supports batch <= 4 (use mode 0)");
   const int padded = (rt.enable_cuda_graph && !fused) ? bucket_for(bs) : bs;
   if (padded < 0 || padded > max_bs) return fail("batch exceeds max_batch bucket");
@@ -836,7 +886,7 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
 // are staged on the device up front, each step's token id is the previous step's on-device arg-max,
 // and there is no host synchronisation inside the timed region (CUDA events on the launch stream).
 bool Qwen3Model::decode_burst(int kv_id, uint32_t first_token, int K, uint32_t* tokens_out, float* ms_total) {
-  if (!finalized || rt.mode != 1) return fail("decode_burst needs the fused path");
+  if (!finalized || rt.mode < 1) return fail("decode_burst needs the fused path");
   if (K <= 0) return fail("K must be positive");
   DeviceBuf staged;
   if (!staged.alloc_zeros((size_t)K * meta_bytes)) return fail("burst staging alloc failed");
@@ -880,7 +930,7 @@ bool Qwen3Model::decode_burst(int kv_id, uint32_t first_token, int K, uint32_t* 
 // `iters` times, timed with CUDA events: the roofline leg of bench.py (weights >> L2, so every pass is
 // cold).  Returns ms per pass and the number of GEMV launches per pass.
 bool Qwen3Model::bench_gemv_pass(int iters, float* ms_per_pass, int* launches_per_pass) {
-  if (!finalized || rt.mode != 1 || tp.is_sharded()) return fail("bench_gemv_pass needs the fused single-GPU path");
+  if (!finalized || rt.mode < 1 || tp.is_sharded()) return fail("bench_gemv_pass needs the fused single-GPU path");
   const Config& c = config;
   const int H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim(), I = local_inter();
   cudaStream_t st = ctx.stream;
@@ -986,7 +1036,7 @@ __attribute__((visibility("default"))) void* pq_model_create(const pq_config* c,
   if (c->head_dim != 128) return bail("head_dim must be 128 (HEAD_DIM is hard-coded in the reference kernels too)");
   e = m->k.load(kernel_lib_path);
   if (!e.empty()) return bail(e);
-  if (m->rt.mode == 1 && !m->k.has_extensions())
+  if (m->rt.mode >= 1 && !m->k.has_extensions())
     return bail("fused mode needs the B200 extensions; this kernel library only has the reference ABI");
   // DeviceContext::new_with_device (tensor.rs:23-59)
   if (m->k.cuda_set_device(r->device_ordinal) != 0) return bail("cuda_set_device failed (no CUDA device?)");

@@ -62,6 +62,7 @@ EXT_SIGNATURES = {
     "pk_b200_set_pdl": (None, [i32]),
     "pk_b200_gemv_fused": (i32, [C.POINTER(GemvArgs), vp]),
     "pk_b200_set_gemv_tuning": (None, [i32, i32, i32]),
+    "pk_b200_decode_step_persistent": (i32, [vp, vp]),
     "pk_b200_decode_attention_fused": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7 + [i64, f32, vp]),
     "pk_tp_flag_bytes": (i64, []),
     "pk_tp_comm_create": (vp, [i32, i32, C.POINTER(vp), C.POINTER(vp), i64]),

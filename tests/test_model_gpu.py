@@ -21,7 +21,9 @@ pytestmark = pytest.mark.gpu
 REF_LIB = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libkernels_ref.so"))
 TOL_ULP = 6  # logits, in bf16 ulps at the row's max |logit| (tiny/small configs, <= 4 layers)
 
-VARIANTS = [("fused", dict(fused=True)), ("compat", dict(fused=False)),
+VARIANTS = [("fused", dict(fused=True)), ("persistent", dict(fused=True, persistent=True)),
+            ("persistent-nograph", dict(fused=True, persistent=True, enable_cuda_graph=False)),
+            ("compat", dict(fused=False)),
             ("compat-nograph", dict(fused=False, enable_cuda_graph=False))]
 if os.path.exists(REF_LIB):
     VARIANTS.append(("refkernels", dict(fused=False, kernel_lib=REF_LIB)))
@@ -57,7 +59,7 @@ def test_tiny_prefill_decode_parity(name, kw):
         assert ok, f"{name} step {step}: {info}"
 
 
-@pytest.mark.parametrize("name,kw", VARIANTS[:2])
+@pytest.mark.parametrize("name,kw", [VARIANTS[0], VARIANTS[3]])
 def test_small_config_parity(name, kw):
     """4 layers, GQA group 2, untied lm_head, prompt crossing several pages."""
     got, want, _ = run_teacher_forced(QWEN3_SMALL, kw, prompt_len=70, n_decode=6)
@@ -66,7 +68,7 @@ def test_small_config_parity(name, kw):
         assert ok, f"{name} step {step}: {info}"
 
 
-@pytest.mark.parametrize("name,kw", VARIANTS[:2])
+@pytest.mark.parametrize("name,kw", [VARIANTS[0], VARIANTS[1], VARIANTS[3]])
 def test_long_context_split_kv_path(name, kw):
     """ctx >= 1024 at bs=1 takes the split-KV path in the reference (batch_decode_buffers.rs:281-287)."""
     got, want, orc = run_teacher_forced(QWEN3_TINY, kw, prompt_len=1030, n_decode=3, num_pages=128)
