@@ -211,7 +211,7 @@ def run_ours(args, cfg, rank, world, dist):
         raise SystemExit(f"prompt {prompt_len} + steps exceed the reference's 4096-position RoPE table")
     pages = 3 * (ctx_max // 16 + 2) + 8
     tp_comm = make_tp_comm(rank, world, dist, max_tokens=256, hidden=cfg.hidden_size) if world > 1 else None
-    persistent = world == 1 and os.environ.get("PK_DECODE", "persistent") == "persistent"
+    persistent = world == 1 and os.environ.get("PK_DECODE", "fused") == "persistent"
     rt = ModelRuntimeConfig(enable_cuda_graph=True, tensor_parallel=TensorParallelConfig(rank, world),
                             device_ordinal=local_rank, fused=True, persistent=persistent, num_pages=pages,
                             max_batch=1, enable_pdl=True)

@@ -145,6 +145,36 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   const int hi = min(len, lo + chunk);
   const int* pages = a.page_indices + a.page_indptr[b];
 
+  // Let the next kernel (the o_proj GEMV) become resident and prefetch its weights while we run.
+  pdl_launch_dependents();
+
+  // Fused path: the cached K/V rows of round 0 do not depend on the previous kernel (the step's own
+  // token is injected from shared memory, never read from the cache), so request them BEFORE
+  // griddepcontrol.wait: their HBM latency overlaps the tail of the qkv GEMV.
+  constexpr int kRoundTokens = kTokPerStep * kUnroll;
+  uint4 kr0[kUnroll], vr0[kUnroll];
+  bool ok0[kUnroll];
+  const bool early = a.fused != 0 && a.page_size == 16;
+  if (early) {
+    const int pos_e = a.positions[b];
+    const int64_t kvh_off = (int64_t)kvh * HD + l16 * 8;
+    int pg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pg[i] = (lo + 16 * i < hi) ? __ldg(pages + (lo >> 4) + i) : 0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int t = lo + warp * 2 + half + u * kTokPerStep;
+      ok0[u] = t < hi && t != pos_e;
+      kr0[u] = make_uint4(0, 0, 0, 0);
+      vr0[u] = make_uint4(0, 0, 0, 0);
+      if (ok0[u]) {
+        const int64_t off = (int64_t)pg[u >> 1] * a.stride_page + (int64_t)(t & 15) * a.nkv * HD + kvh_off;
+        kr0[u] = ldg_stream(a.kv + a.k_off + off);
+        vr0[u] = ldg_stream(a.kv + a.v_off + off);
+      }
+    }
+  }
+
   pdl_wait();
 
   // ---- query heads of this kv head -> registers (fp32) ----
@@ -193,26 +223,35 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): iterate on the CTA's round
   // base and let each half-warp mask its own tokens.  A round is 64 tokens = 4 pages: the 4 page ids
   // are fetched first (one latency), then all 8 K and 8 V rows of the half-warp (one latency).
-  for (int round = lo; round < hi; round += kTokPerStep * kUnroll) {
+  for (int round = lo; round < hi; round += kRoundTokens) {
     const int base = round + warp * 2 + half;
-    int pg[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pg[i] = (round + 16 * i < hi) ? __ldg(pages + (round >> 4) + i) : 0;
     uint4 kr[kUnroll], vr[kUnroll];
     bool ok[kUnroll];
+    if (early && round == lo) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int t = base + u * kTokPerStep;
-      ok[u] = t < hi && t != new_pos;
-      kr[u] = make_uint4(0, 0, 0, 0);
-      vr[u] = make_uint4(0, 0, 0, 0);
-      if (ok[u]) {
-        // (t - round) / 16 == u / 2 because warp*2+half < 8; page_size is 16 on this path
-        const int page = a.page_size == 16 ? pg[u >> 1] : __ldg(pages + t / a.page_size);
-        const int slot = t % a.page_size;
-        const int64_t off = (int64_t)page * a.stride_page + (int64_t)slot * a.nkv * HD;
-        kr[u] = ldg_stream(kbase + off);
-        vr[u] = ldg_stream(vbase + off);
+      for (int u = 0; u < kUnroll; ++u) {
+        kr[u] = kr0[u];
+        vr[u] = vr0[u];
+        ok[u] = ok0[u];
+      }
+    } else {
+      int pg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pg[i] = (round + 16 * i < hi) ? __ldg(pages + (round >> 4) + i) : 0;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int t = base + u * kTokPerStep;
+        ok[u] = t < hi && t != new_pos;
+        kr[u] = make_uint4(0, 0, 0, 0);
+        vr[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          // (t - round) / 16 == u / 2 because warp*2+half < 8; page_size is 16 on this path
+          const int page = a.page_size == 16 ? pg[u >> 1] : __ldg(pages + t / a.page_size);
+          const int slot = t % a.page_size;
+          const int64_t off = (int64_t)page * a.stride_page + (int64_t)slot * a.nkv * HD;
+          kr[u] = ldg_stream(kbase + off);
+          vr[u] = ldg_stream(vbase + off);
+        }
       }
     }
     float s[GROUP][kUnroll];

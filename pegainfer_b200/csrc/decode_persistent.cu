@@ -53,6 +53,7 @@ struct PersistArgs {
   unsigned* amax_ticket;
   int* sample_out;
   int kc, stages;
+  unsigned long long* dbg;  // optional: per-phase globaltimer stamps of CTA 0 (profiling builds of the host)
 };
 
 __device__ __forceinline__ uint4 ld_cg16(const void* p) {
@@ -278,6 +279,16 @@ __device__ __forceinline__ void consume_gemv(const PersistArgs& a, const Smem& s
   }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PK_STAMP(slot)                                                                   \
+  do {                                                                                   \
+    if (a.dbg && tid == 0 && blockIdx.x == 0 && li < 4) a.dbg[li * 16 + (slot)] = gtimer(); \
+  } while (0)
+
 // ---------------------------------------------------------------- grid barrier (consumer warps only)
 __device__ __forceinline__ void grid_barrier(const PersistArgs& a, unsigned& epoch, int tid) {
   __threadfence();
@@ -336,15 +347,25 @@ struct AttScratch {  // per team, aliased on the xs region
   int last;
 };
 
-__device__ void attention_item(const PersistArgs& a, const PersistLayer& L, int layer, int chunk_idx, int kvh, int chunk,
-                               int nchunks, int len, AttScratch* S, int team, int twarp, int lane) {
+constexpr int kU = 8;  // K/V rows per half-warp per 64-token round
+
+// Per-step, per-lane addressing of round 0 of this team's attention item: identical for every layer (the
+// page table is fixed within a step), so it is computed once and the K/V rows of layer l are requested
+// BEFORE the qkv GEMV of layer l -- their HBM latency (several us while the weight stream saturates the
+// memory system) hides behind that GEMV instead of sitting on the attention phase's critical path.
+struct KvPrefetch {
+  int64_t off[kU];   // element offset inside a layer's K (or V) plane; < 0: masked token
+};
+
+__device__ __forceinline__ void attention_item(const PersistArgs& a, const PersistLayer& L, int layer, int chunk_idx,
+                                               int kvh, int chunk, int nchunks, int len, int pos,
+                                               AttScratch* S, int team, int twarp, int lane, bool prefetched,
+                                               const KvPrefetch& pf) {
   constexpr int GROUP = 4;
-  constexpr int kU = 8;
   const int half = lane >> 4, l16 = lane & 15;
   const int t128 = twarp * 32 + lane;
   const int lo = chunk_idx * chunk, hi = min(len, lo + chunk);
-  const int* pages = a.page_indices + a.page_indptr[0];
-  const int pos = a.positions[0];
+  const int* pages = a.page_indices + __ldg(a.page_indptr);
   const int64_t k_off = (int64_t)layer * a.layer_stride, v_off = k_off + a.kv_block_len;
 
   // q heads (and the new k/v when this chunk owns the position)
@@ -377,21 +398,36 @@ __device__ void attention_item(const PersistArgs& a, const PersistLayer& L, int 
   const bf16* vbase = a.kv + v_off + (int64_t)kvh * P_HD + l16 * 8;
   for (int round = lo; round < hi; round += 8 * kU) {
     const int base = round + twarp * 2 + half;
-    int pg[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pg[i] = (round + 16 * i < hi) ? __ldg(pages + (round >> 4) + i) : 0;
     uint4 kr[kU], vr[kU];
     bool ok[kU];
+    if (prefetched && round == lo) {  // addresses precomputed once per step, lines already in L2
+      const bf16* kl = a.kv + k_off;
+      const bf16* vl = a.kv + v_off;
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int t = base + u * 8;
-      ok[u] = t < hi && t != new_pos;
-      kr[u] = make_uint4(0, 0, 0, 0);
-      vr[u] = make_uint4(0, 0, 0, 0);
-      if (ok[u]) {
-        const int64_t off = (int64_t)pg[u >> 1] * a.stride_page + (int64_t)(t & 15) * a.nkv * P_HD;
-        kr[u] = ld_cg16(kbase + off);  // the cache is rewritten every step: never through L1
-        vr[u] = ld_cg16(vbase + off);
+      for (int u = 0; u < kU; ++u) {
+        ok[u] = pf.off[u] >= 0;
+        kr[u] = make_uint4(0, 0, 0, 0);
+        vr[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          kr[u] = ld_cg16(kl + pf.off[u]);
+          vr[u] = ld_cg16(vl + pf.off[u]);
+        }
+      }
+    } else {
+      int pg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pg[i] = (round + 16 * i < hi) ? __ldg(pages + (round >> 4) + i) : 0;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = base + u * 8;
+        ok[u] = t < hi && t != new_pos;
+        kr[u] = make_uint4(0, 0, 0, 0);
+        vr[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          const int64_t off = (int64_t)pg[u >> 1] * a.stride_page + (int64_t)(t & 15) * a.nkv * P_HD;
+          kr[u] = ld_cg16(kbase + off);  // the cache is rewritten every step: never through L1
+          vr[u] = ld_cg16(vbase + off);
+        }
       }
     }
     float s[GROUP][kU];
@@ -611,28 +647,79 @@ __global__ void __launch_bounds__(PTHREADS_C + 32, 1) decode_step_persistent_ker
   AttScratch* scratch = reinterpret_cast<AttScratch*>(reinterpret_cast<uint8_t*>(sm.xs) +
                                                       (size_t)team * ((sizeof(AttScratch) + 127) & ~(size_t)127));
 
+  // this team's first attention item and its round-0 addressing (same for every layer)
+  const int pos = a.positions[0];
+  const int item0 = blockIdx.x * 2 + team;
+  const bool has_item0 = item0 < nchunks * a.nkv;
+  KvPrefetch pf;
+  {
+    const int half = lane >> 4, l16 = lane & 15;
+    const int cidx = item0 / a.nkv, kvh0 = item0 % a.nkv;
+    const int lo = cidx * chunk, hi = min(len, lo + chunk);
+    const int* pages = a.page_indices + a.page_indptr[0];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int t = lo + twarp * 2 + half + u * 8;
+      pf.off[u] = -1;
+      if (has_item0 && t < hi && t != pos)
+        pf.off[u] = (int64_t)__ldg(pages + (t >> 4)) * a.stride_page + (int64_t)(t & 15) * a.nkv * P_HD +
+                    (int64_t)kvh0 * P_HD + l16 * 8;
+    }
+  }
+
   for (int li = 0; li < a.num_layers; ++li) {
     const PersistLayer L = a.layers[li];
+    // pull this layer's K/V rows into L2 now (no registers held: 9 warps x 168 registers is the budget);
+    // the attention phase after the qkv GEMV and the grid barrier then hits L2 instead of queueing
+    // behind the saturated weight stream in DRAM
+    {
+      const bf16* kl = a.kv + (int64_t)li * a.layer_stride;
+      const bf16* vl = kl + a.kv_block_len;
+      if ((lane & 7) == 0) {  // one prefetch per 128-byte line (a 256-byte row = 2 lines)
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (pf.off[u] >= 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kl + pf.off[u]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vl + pf.off[u]));
+          }
+      }
+    }
     // P1: q|k|v = W_qkv . RMSNorm(h + residual); Hnext = h + residual
+    PK_STAMP(0);
     stage_x_norm(a, sm, h_in, residual, L.in_ln, Hnext, a.H, tid, warp, lane);
+    PK_STAMP(1);
     consume_gemv<0>(a, sm, ring, a.qd + 2 * a.kd, a.H, a.q, a.k, a.v, a.qd, a.qd + a.kd, warp, lane, nullptr, nullptr);
+    PK_STAMP(2);
     grid_barrier(a, epoch, tid);
+    PK_STAMP(3);
     // P2: attention items (chunk, kv head), two teams per CTA
-    for (int item = blockIdx.x * 2 + team; item < nchunks * a.nkv; item += gridDim.x * 2)
-      attention_item(a, L, li, item / a.nkv, item % a.nkv, chunk, nchunks, len, scratch, team, twarp, lane);
+    for (int item = item0; item < nchunks * a.nkv; item += gridDim.x * 2)
+      attention_item(a, L, li, item / a.nkv, item % a.nkv, chunk, nchunks, len, pos, scratch, team, twarp, lane,
+                     item == item0, pf);
+    PK_STAMP(4);
     grid_barrier(a, epoch, tid);
+    PK_STAMP(5);
     // P3: attn_proj = W_o . attn_out
     stage_x_plain(sm, a.attn_out, a.qd, tid);
+    PK_STAMP(6);
     consume_gemv<0>(a, sm, ring, a.H, a.qd, a.attn_proj, nullptr, nullptr, a.H, a.H, warp, lane, nullptr, nullptr);
+    PK_STAMP(7);
     grid_barrier(a, epoch, tid);
+    PK_STAMP(8);
     // P4: act = SwiGLU(W_gate_up . RMSNorm(Hnext + attn_proj)); Hcur = Hnext + attn_proj
     stage_x_norm(a, sm, Hnext, a.attn_proj, L.post_ln, Hcur, a.H, tid, warp, lane);
+    PK_STAMP(9);
     consume_gemv<1>(a, sm, ring, a.I, a.H, a.mlp_act, nullptr, nullptr, 0, 0, warp, lane, nullptr, nullptr);
+    PK_STAMP(10);
     grid_barrier(a, epoch, tid);
+    PK_STAMP(11);
     // P5: mlp_out = W_down . act
     stage_x_plain(sm, a.mlp_act, a.I, tid);
+    PK_STAMP(12);
     consume_gemv<0>(a, sm, ring, a.H, a.I, a.mlp_out, nullptr, nullptr, a.H, a.H, warp, lane, nullptr, nullptr);
+    PK_STAMP(13);
     grid_barrier(a, epoch, tid);
+    PK_STAMP(14);
     h_in = Hcur;
     residual = a.mlp_out;
   }
@@ -711,6 +798,7 @@ extern "C" int pk_b200_decode_step_persistent(const pk_b200_decode_step_args* g,
   a.amax_val = reinterpret_cast<float*>(ctl + 16);
   a.amax_idx = reinterpret_cast<int*>(ctl + 16 + 256);
   a.sample_out = g->sample_out;
+  a.dbg = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(g->sync_scratch) + 4096);  // [4 layers][16]
   const int sms = sm_count();
   if (sms > 256 || g->page_size != 16) return -1;
   a.kc = 4096;

@@ -57,6 +57,18 @@ DeviceBuf& DeviceBuf::operator=(DeviceBuf&& o) noexcept {
 DeviceBuf::~DeviceBuf() {
   if (ptr) cudaFree(ptr);
 }
+bool DeviceBuf::alloc_uninit(size_t nbytes) {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+  if (nbytes == 0) nbytes = 16;
+  if (cudaMalloc(&ptr, nbytes) != cudaSuccess) {
+    ptr = nullptr;
+    return false;
+  }
+  bytes = nbytes;
+  return true;
+}
 bool DeviceBuf::alloc_zeros(size_t nbytes) {
   if (ptr) cudaFree(ptr);
   ptr = nullptr;
@@ -231,6 +243,10 @@ struct Qwen3Model {
   bool decode_kernels_fused(int bs);
   bool decode_kernels_persistent();
   DeviceBuf layer_ptrs_d, sync_scratch;
+  HiddenStates pf_hid, pf_hid_out, pf_nrm, pf_q, pf_k, pf_v, pf_o, pf_gu, pf_act, pf_att;
+  DeviceBuf pf_plan;
+  std::vector<int> plan_pack;
+  int prefill_capacity = 0;
   bool ensure_capacity(KvState& s, int tokens);
   bool sample_greedy(const pk_bf16* logits, int* out);
   ~Qwen3Model();
@@ -423,6 +439,21 @@ bool Qwen3Model::create_decode_buffers() {
   ok = ok && sample_out.alloc_zeros(64 * 4) && top1_val.alloc_zeros(64) && top1_states.alloc_zeros(1 << 20) &&
        cudaMallocHost((void**)&sample_h, 64 * 4) == cudaSuccess;
   if (!ok) return fail(std::string("decode buffer allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rt.mode == 2) {  // persistent decode: device table of per-layer weight pointers + sync scratch
+    std::vector<pk_b200_layer_ptrs> lp(c.num_hidden_layers);
+    for (int i = 0; i < c.num_hidden_layers; ++i) {
+      TransformerBlock& L = layers[i];
+      lp[i] = pk_b200_layer_ptrs{L.attention.qkv_proj.data.bf(), L.attention.o_proj.data.bf(),
+                                 L.mlp.gate_up_proj.data.bf(), L.mlp.down_proj.data.bf(),
+                                 L.input_layernorm.data.bf(), L.post_attention_layernorm.data.bf(),
+                                 L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf()};
+    }
+    if (!layer_ptrs_d.alloc_zeros(lp.size() * sizeof(pk_b200_layer_ptrs)) || !sync_scratch.alloc_zeros(8192))
+      return fail("persistent decode scratch allocation failed");
+    if (!cu(cudaMemcpy(layer_ptrs_d.ptr, lp.data(), lp.size() * sizeof(pk_b200_layer_ptrs), cudaMemcpyHostToDevice),
+            "layer pointer upload"))
+      return false;
+  }
   return true;
 }
 
@@ -498,18 +529,32 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
             o_qt = put(qo_tile), o_kt = put(kv_tile), o_tnr = put(std::vector<int>{T});
   const int o_tok = (int)pack.size();
   pack.insert(pack.end(), reinterpret_cast<const int*>(tokens), reinterpret_cast<const int*>(tokens) + T);
-  DeviceBuf plan;
-  if (!plan.alloc_zeros(pack.size() * 4)) return fail("plan alloc failed");
-  if (!cu(cudaMemcpyAsync(plan.ptr, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, ctx.stream), "plan H2D"))
-    return false;
-  const int* P = plan.i32();
+  plan_pack.swap(pack);  // keep the host block alive until the async copy has been consumed
 
-  // ---- PrefillBuffers::new (prefill.rs:30-50) ----
-  HiddenStates hid, hid_out, nrm, qb, kb, vb, ob, gu, act, att;
-  if (!(hid.zeros(H, T) && hid_out.zeros(H, T) && nrm.zeros(H, T) && qb.zeros(qd, T) && kb.zeros(kd, T) &&
-        vb.zeros(kd, T) && ob.zeros(H, T) && gu.zeros(2 * I, T) && act.zeros(I, T) && att.zeros(qd, T)))
-    return fail("prefill buffer allocation failed");
+  // ---- PrefillBuffers (prefill.rs:17-51).  The reference re-allocates nine buffers per prefill call
+  // (its doc comment cites the cuMemAlloc cost in TTFT); here they are a grow-only arena owned by the
+  // model: every element is overwritten before it is read, so no zero fill either. ----
+  if (T > prefill_capacity) {
+    cudaStreamSynchronize(ctx.stream);
+    const int cap = ((T + 255) / 256) * 256;
+    auto grow = [&](HiddenStates& hs, size_t dim) {
+      hs.hidden_dim = dim;
+      hs.seq_len = cap;
+      return hs.data.alloc_uninit(dim * cap * 2);
+    };
+    if (!(grow(pf_hid, H) && grow(pf_hid_out, H) && grow(pf_nrm, H) && grow(pf_q, qd) && grow(pf_k, kd) &&
+          grow(pf_v, kd) && grow(pf_o, H) && grow(pf_gu, 2 * I) && grow(pf_act, I) && grow(pf_att, qd) &&
+          pf_plan.alloc_uninit((size_t)cap * 16 + (size_t)max_total_pages * 4 + 65536)))
+      return fail("prefill buffer allocation failed");
+    prefill_capacity = cap;
+  }
+  HiddenStates &hid = pf_hid, &hid_out = pf_hid_out, &nrm = pf_nrm, &qb = pf_q, &kb = pf_k, &vb = pf_v, &ob = pf_o,
+               &gu = pf_gu, &act = pf_act, &att = pf_att;
   cudaStream_t st = ctx.stream;
+  if (plan_pack.size() * 4 > pf_plan.bytes) return fail("prefill plan larger than its buffer");
+  if (!cu(cudaMemcpyAsync(pf_plan.ptr, plan_pack.data(), plan_pack.size() * 4, cudaMemcpyHostToDevice, st), "plan H2D"))
+    return false;
+  const int* P = pf_plan.i32();
   const float eps = c.rms_norm_eps;
   const float sm_scale = 1.0f / sqrtf((float)hd);
   k.embedding_batched_cuda(embed_tokens.data.bf(), reinterpret_cast<const uint32_t*>(P + o_tok), hid.data.bf(), H, T, st);
@@ -721,21 +766,7 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
 // mode 2: the whole token in one cooperative launch (decode_persistent.cu)
 bool Qwen3Model::decode_kernels_persistent() {
   const Config& c = config;
-  if (!layer_ptrs_d.ptr) {
-    std::vector<pk_b200_layer_ptrs> lp(c.num_hidden_layers);
-    for (int i = 0; i < c.num_hidden_layers; ++i) {
-      TransformerBlock& L = layers[i];
-      lp[i] = pk_b200_layer_ptrs{L.attention.qkv_proj.data.bf(), L.attention.o_proj.data.bf(),
-                                 L.mlp.gate_up_proj.data.bf(), L.mlp.down_proj.data.bf(),
-                                 L.input_layernorm.data.bf(), L.post_attention_layernorm.data.bf(),
-                                 L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf()};
-    }
-    if (!layer_ptrs_d.alloc_zeros(lp.size() * sizeof(pk_b200_layer_ptrs)) || !sync_scratch.alloc_zeros(8192))
-      return fail("persistent decode scratch allocation failed");
-    if (!cu(cudaMemcpy(layer_ptrs_d.ptr, lp.data(), lp.size() * sizeof(pk_b200_layer_ptrs), cudaMemcpyHostToDevice),
-            "layer pointer upload"))
-      return false;
-  }
+  if (!layer_ptrs_d.ptr) return fail("persistent decode buffers were not created");
   const int* M = meta_d.i32();
   pk_b200_decode_step_args g{};
   g.layers_dev = layer_ptrs_d.ptr;
@@ -1114,6 +1145,7 @@ __attribute__((visibility("default"))) void* pq_debug_buffer(void* mp, const cha
   if (n == "logits") return m->logits.data.ptr;
   if (n == "kv") return m->kv_buffer.ptr;
   if (n == "attn_out") return m->attn_out.data.ptr;
+  if (n == "persist_dbg") return m->sync_scratch.ptr ? static_cast<char*>(m->sync_scratch.ptr) + 4096 : nullptr;
   return nullptr;
 }
 

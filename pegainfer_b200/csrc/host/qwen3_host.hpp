@@ -65,6 +65,7 @@ struct DeviceBuf {  // owning CudaSlice<T>
   DeviceBuf& operator=(DeviceBuf&& o) noexcept;
   ~DeviceBuf();
   bool alloc_zeros(size_t nbytes);
+  bool alloc_uninit(size_t nbytes);
   pk_bf16* bf() const { return static_cast<pk_bf16*>(ptr); }
   int* i32() const { return static_cast<int*>(ptr); }
 };
