@@ -172,6 +172,12 @@ int64_t pk_b200_launch_count(int reset);
 /* Enable (1) / disable (0) programmatic dependent launch on this thread's launches. */
 void pk_b200_set_pdl(int enable);
 
+/* Tensor-core GEMM with up to three output segments (the fused q|k|v projection of prefill):
+ * rows [0, seg_rows[0]) of W -> Y[0] (a HiddenStates [seg_rows[0], N]), the next seg_rows[1] -> Y[1], the
+ * rest -> Y[2].  seg_rows must sum to M.  Same arithmetic as gemm_cuda. */
+int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16* const* Y, const int* seg_rows, int M, int N,
+                          int K, pk_stream stream);
+
 /* GEMV with fused prologue/epilogue for decode (N == 1..4 tokens), one launch:
  *   x_mode 0: x = X as is ([N, K]).
  *   x_mode 1: X is `hidden` [N, K]; x = RMSNorm(hidden + residual) * norm_w computed in the
@@ -181,7 +187,13 @@ void pk_b200_set_pdl(int enable);
  *   epi 0:    Y = bf16(W x); rows are routed to up to three outputs: rows [0, seg_rows[0]) ->
  *             Y[0], the next seg_rows[1] -> Y[1], the rest -> Y[2] (the fused q|k|v projection).
  *   epi 1:    SwiGLU: W = [M gate rows | M up rows];
- *             Y[0][m] = bf16(silu(bf16(gate_m.x)) * bf16(up_m.x))  (csrc/fused_proj.cu:44-63). */
+ *             Y[0][m] = bf16(silu(bf16(gate_m.x)) * bf16(up_m.x))  (csrc/fused_proj.cu:44-63).
+ *   Tensor parallel, GEMV fused with its all-reduce over NVLink peer memory (no collective launch):
+ *   epi 2:    the bf16 partial rows are pushed into every rank's staging slot and the grid's last CTA
+ *             publishes the sequence flag (release.sys); Y is not written.
+ *   x_mode 2: like x_mode 1, but `residual` is the all-reduce result: after all ranks' flags are seen the
+ *             prologue sums the `world` partials from local staging in rank order (fp32, one bf16 rounding),
+ *             adds the residual stream X and applies RMSNorm.  Pairs with the previous epi-2 launch. */
 typedef struct {
   const pk_bf16* W;
   const pk_bf16* X;
@@ -195,6 +207,7 @@ typedef struct {
   pk_bf16* hidden_out;
   pk_bf16* normed_out;
   int epi;
+  void* tp_comm; /* pk_tp_comm*, required for x_mode 2 / epi 2 (tensor parallel) */
 } pk_b200_gemv_args;
 int pk_b200_gemv_fused(const pk_b200_gemv_args* args, pk_stream stream);
 /* Ring depth (2..12 stages of 8 row segments), CTAs per SM and K elements per row segment (multiple of

@@ -148,4 +148,30 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
       : "memory");
 }
 
+// ---- tensor-parallel peer-memory communicator (tp_allreduce.cu, gemv.cu) ----
+constexpr int kTpMaxWorld = 8;
+constexpr int kTpMaxCtas = 64;
+constexpr int kTpThreads = 512;
+
+struct TpDev {
+  uint8_t* stage[kTpMaxWorld];   // stage[p]: rank p's staging base as mapped in THIS process
+  uint32_t* flags[kTpMaxWorld];  // flags[p]: rank p's flag array  [2][kTpMaxCtas][world] + ctl
+  int rank, world;
+  int64_t slot_bytes;            // bytes per (slot, src) region
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 }  // namespace pk
+
+struct pk_tp_comm {
+  pk::TpDev d;
+  int64_t staging_bytes;
+};

@@ -138,7 +138,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-               bf16* __restrict__ Y, int M /*features*/, int N /*tokens*/, int K) {
+               bf16* __restrict__ Y, bf16* __restrict__ Y1, bf16* __restrict__ Y2, int e0, int e1,
+               int M /*features*/, int N /*tokens*/, int K) {
+  // Output features [0,e0) go to Y (row length e0), [e0,e1) to Y1, [e1,M) to Y2: the fused q|k|v
+  // projection writes three HiddenStates buffers from one launch (e0 == e1 == M: plain GEMM).
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -223,7 +226,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const bool vec_ok = (M % 8 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+    const bool vec_ok = (e0 % 32 == 0) && (e1 % 32 == 0) && (M % 8 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(Y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Y2) & 15) == 0);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int mb = tile % m_tiles, nb = tile / m_tiles;
@@ -238,7 +242,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         tmem_ld32(t_row + (uint32_t)c, v);
         const int f0 = nb * BN + c;
         if (tok < N && f0 < M) {
-          bf16* dst = Y + (size_t)tok * M + f0;
+          bf16* dst;
+          if (f0 < e0) dst = Y + (size_t)tok * e0 + f0;
+          else if (f0 < e1) dst = Y1 + (size_t)tok * (e1 - e0) + (f0 - e0);
+          else dst = Y2 + (size_t)tok * (M - e1) + (f0 - e1);
           if (vec_ok && f0 + 32 <= M) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -250,7 +257,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               reinterpret_cast<uint4*>(dst)[j] = o;
             }
           } else {
-            for (int j = 0; j < 32 && f0 + j < M; ++j) dst[j] = f2bf(__uint_as_float(v[j]));
+            for (int j = 0; j < 32 && f0 + j < M; ++j) {
+              const int f = f0 + j;
+              bf16* d1 = f < e0 ? Y + (size_t)tok * e0 + f
+                                : (f < e1 ? Y1 + (size_t)tok * (e1 - e0) + (f - e0) : Y2 + (size_t)tok * (M - e1) + (f - e1));
+              *d1 = f2bf(__uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -302,8 +314,8 @@ static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int bo
 }
 
 template <int BN, int STAGES>
-static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16* Y, int M, int N,
-                             int K, cudaStream_t stream) {
+static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16* Y, bf16* Y1, bf16* Y2, int e0,
+                             int e1, int M, int N, int K, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
   auto kern = gemm_tc_kernel<BN, STAGES>;
   static thread_local bool configured = false;
@@ -313,7 +325,7 @@ static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16*
   }
   const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
   int grid = tiles < sm_count() ? tiles : sm_count();
-  return launch(kern, dim3(grid), dim3(kGemmThreads), smem, stream, true, mx, mw, Y, M, N, K);
+  return launch(kern, dim3(grid), dim3(kGemmThreads), smem, stream, true, mx, mw, Y, Y1, Y2, e0, e1, M, N, K);
 }
 
 static int gemm_impl_mode() {  // 0 tcgen05 (default), 1 simt
@@ -325,7 +337,15 @@ static int gemm_impl_mode() {  // 0 tcgen05 (default), 1 simt
   return mode;
 }
 
+void launch_gemm_seg(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K,
+                     cudaStream_t stream);
+
 void launch_gemm(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K, cudaStream_t stream) {
+  launch_gemm_seg(W, X, Y, Y, Y, M, M, M, N, K, stream);
+}
+
+void launch_gemm_seg(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K,
+                     cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return;
   const bool tma_ok = K % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(X) & 15) == 0;
@@ -336,14 +356,21 @@ void launch_gemm(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K, cud
     CUtensorMap mx, mw;
     if (make_map(&mx, X, N, K, BM) && make_map(&mw, W, M, K, bn)) {
       if (small)
-        launch_tc<128, 6>(mx, mw, Y, M, N, K, stream);
+        launch_tc<128, 6>(mx, mw, Y, Y1, Y2, e0, e1, M, N, K, stream);
       else
-        launch_tc<256, 4>(mx, mw, Y, M, N, K, stream);
+        launch_tc<256, 4>(mx, mw, Y, Y1, Y2, e0, e1, M, N, K, stream);
       return;
     }
   }
-  launch(gemm_simt_kernel, dim3((M + 63) / 64, (N + 63) / 64), dim3(256), 0, stream, true, W, X, Y,
-         M, N, K);
+  // SIMT fallback: one launch per segment (row slices of W are contiguous)
+  const int starts[3] = {0, e0, e1}, ends[3] = {e0, e1, M};
+  bf16* outs[3] = {Y, Y1, Y2};
+  for (int sgi = 0; sgi < 3; ++sgi) {
+    const int m = ends[sgi] - starts[sgi];
+    if (m <= 0) continue;
+    launch(gemm_simt_kernel, dim3((m + 63) / 64, (N + 63) / 64), dim3(256), 0, stream, true,
+           W + (size_t)starts[sgi] * K, X, outs[sgi], m, N, K);
+  }
 }
 
 // defined in gemv.cu
@@ -353,6 +380,15 @@ void launch_gemv_generic(const bf16* W, const bf16* X, bf16* Y, int M, int N, in
                          cudaStream_t stream);
 
 }  // namespace pk
+
+// Fused multi-output projection (q|k|v from the stacked qkv_proj): rows [0,seg_rows[0]) -> Y[0], ...
+extern "C" int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16* const* Y, const int* seg_rows, int M,
+                                     int N, int K, pk_stream stream) {
+  if (!W || !X || !Y || !seg_rows || seg_rows[0] + seg_rows[1] + seg_rows[2] != M) return -1;
+  pk::launch_gemm_seg((const pk::bf16*)W, (const pk::bf16*)X, (pk::bf16*)Y[0], (pk::bf16*)(Y[1] ? Y[1] : Y[0]),
+                      (pk::bf16*)(Y[2] ? Y[2] : Y[0]), seg_rows[0], seg_rows[0] + seg_rows[1], M, N, K, stream);
+  return 0;
+}
 
 extern "C" void gemm_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
                           pk_stream stream) {

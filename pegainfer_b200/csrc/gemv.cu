@@ -38,7 +38,8 @@ struct GemvArgs {
   float eps;
   bf16* hidden_out;
   bf16* normed_out;
-  int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows)
+  int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows), 2 push partial rows to all TP peers
+  TpDev tp;     // x_mode 2 / epi 2: peer staging + flags
   int stages;
   int kc;       // K elements per row segment per stage (multiple of 256); stage = 8 segments
 };
@@ -72,6 +73,7 @@ gemv_stream_kernel(const GemvArgs a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + x_bytes);
   uint64_t* empty = full + kMaxStages;
   float* red = reinterpret_cast<float*>(empty + kMaxStages);  // 64 floats: reductions / SwiGLU swap
+  float* ybuf = red + 64;                                      // epi 2: [NTOK][64] partial rows of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
@@ -137,8 +139,24 @@ gemv_stream_kernel(const GemvArgs a) {
     } else {
       // x = bf16((h + r) * rsqrt(mean((h+r)^2) + eps) * w); hidden_out = bf16(h + r).
       // One pass over global memory: each thread keeps its <= 5 vectors of the row in registers.
+      // x_mode 2 (tensor parallel): r is the all-reduce of the peers' partial rows, summed here from the
+      // local staging slots in rank order (fp32, one bf16 rounding == the collective's bf16 result) after
+      // every rank's release flag for this sequence number has been observed.
       constexpr int kMaxVec = 5;  // K <= 5 * 256 * 8 = 10240
       const int nv = K >> 3;
+      const uint8_t* stage_base = nullptr;
+      if (a.x_mode == 2) {
+        uint32_t* my_flags = a.tp.flags[a.tp.rank];
+        const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(my_flags + 2 * kTpMaxCtas * kTpMaxWorld);
+        const int slot = (int)(seq & 1u);
+        if (tid < a.tp.world) {
+          const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas) * kTpMaxWorld + tid;
+          while (ld_acquire_sys(f) != seq) {
+          }
+        }
+        consumer_bar();
+        stage_base = a.tp.stage[a.tp.rank] + (size_t)slot * a.tp.world * a.tp.slot_bytes;
+      }
       for (int n = 0; n < NTOK; ++n) {
         const uint4* h4 = reinterpret_cast<const uint4*>(a.X + (size_t)n * K);
         const uint4* r4 = reinterpret_cast<const uint4*>(a.residual + (size_t)n * K);
@@ -148,7 +166,21 @@ gemv_stream_kernel(const GemvArgs a) {
         for (int j = 0; j < kMaxVec; ++j) {
           const int i = tid + j * kConsumerThreads;
           if (i < nv) {
-            const uint4 h = h4[i], r = r4[i];
+            const uint4 h = h4[i];
+            uint4 r;
+            if (a.x_mode == 2) {
+              float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              for (int rk = 0; rk < a.tp.world; ++rk) {
+                const uint4 pv = __ldcg(reinterpret_cast<const uint4*>(stage_base + (size_t)rk * a.tp.slot_bytes +
+                                                                       (size_t)n * K * 2) + i);
+                acc8[0] += bf16_lo(pv.x); acc8[1] += bf16_hi(pv.x); acc8[2] += bf16_lo(pv.y); acc8[3] += bf16_hi(pv.y);
+                acc8[4] += bf16_lo(pv.z); acc8[5] += bf16_hi(pv.z); acc8[6] += bf16_lo(pv.w); acc8[7] += bf16_hi(pv.w);
+              }
+              r.x = pack_bf16(acc8[0], acc8[1]); r.y = pack_bf16(acc8[2], acc8[3]);
+              r.z = pack_bf16(acc8[4], acc8[5]); r.w = pack_bf16(acc8[6], acc8[7]);
+            } else {
+              r = r4[i];
+            }
             v[j][0] = bf16_lo(h.x) + bf16_lo(r.x); v[j][1] = bf16_hi(h.x) + bf16_hi(r.x);
             v[j][2] = bf16_lo(h.y) + bf16_lo(r.y); v[j][3] = bf16_hi(h.y) + bf16_hi(r.y);
             v[j][4] = bf16_lo(h.z) + bf16_lo(r.z); v[j][5] = bf16_hi(h.z) + bf16_hi(r.z);
@@ -246,7 +278,12 @@ gemv_stream_kernel(const GemvArgs a) {
     for (int n = 0; n < NTOK; ++n) acc[n] = (acc4[n][0] + acc4[n][1]) + (acc4[n][2] + acc4[n][3]);
 #pragma unroll
     for (int n = 0; n < NTOK; ++n) acc[n] = warp_sum(acc[n]);
-    if (a.epi == 0) {
+    if (a.epi == 2) {
+      if (has_row && lane == 0) {
+#pragma unroll
+        for (int n = 0; n < NTOK; ++n) ybuf[n * 64 + (out_row - r0)] = acc[n];
+      }
+    } else if (a.epi == 0) {
       if (has_row && lane == 0) {
         const int seg = out_row < a.seg_end[0] ? 0 : (out_row < a.seg_end[1] ? 1 : 2);
         const int seg_lo = seg == 0 ? 0 : a.seg_end[seg - 1];
@@ -269,6 +306,40 @@ gemv_stream_kernel(const GemvArgs a) {
           const float up = round_bf16(sw[warp * NTOK + n]);
           a.Y[0][(size_t)n * M + out_row] = f2bf(gt / (1.0f + expf(-gt)) * up);
         }
+      }
+    }
+  }
+  if (a.epi == 2) {
+    // ---- fused GEMV -> all-reduce (push half): store this CTA's partial rows straight into every rank's
+    // staging slot [seq parity][my rank] over NVLink (consumer warp w serves peer w, 32 consecutive rows per
+    // coalesced transaction), then the LAST CTA of the grid publishes the sequence flag to every rank with
+    // release.sys.  The matching reduce + residual add + RMSNorm runs in the prologue (x_mode 2) of the next
+    // GEMV on every rank: no standalone collective kernel.
+    consumer_bar();
+    const int me = a.tp.rank, W = a.tp.world;
+    uint32_t* my_flags = a.tp.flags[me];
+    uint32_t* ctl = my_flags + 2 * kTpMaxCtas * kTpMaxWorld;  // [0] = seq, [2] = CTA ticket of this op
+    const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;  // read after griddepcontrol.wait
+    const int slot = (int)(seq & 1u);
+    const int nrows = r1 - r0;
+    for (int p = warp; p < W; p += kCW) {
+      bf16* dst = reinterpret_cast<bf16*>(a.tp.stage[p] + (size_t)(slot * W + me) * a.tp.slot_bytes);
+#pragma unroll
+      for (int n = 0; n < NTOK; ++n)
+        for (int r = lane; r < nrows; r += 32) dst[(size_t)n * M + r0 + r] = f2bf(ybuf[n * 64 + r]);
+    }
+    __threadfence_system();
+    consumer_bar();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t t = atomicAdd(ctl + 2, 1u);
+      if (t == gridDim.x - 1) {
+        __threadfence_system();
+        for (int p = 0; p < W; ++p)
+          st_release_sys(a.tp.flags[p] + (size_t)(slot * kTpMaxCtas) * kTpMaxWorld + me, seq);
+        ctl[2] = 0;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(ctl) = seq;
       }
     }
   }
@@ -328,7 +399,7 @@ static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
   int kc = g_gemv_kc;
   while (kc > 256 && kc / 2 >= a.K) kc /= 2;  // no point in segments longer than a row
   const size_t x_bytes = (((size_t)NTOK * a.K * 2) + 15) & ~(size_t)15;
-  const size_t tail = 2 * kMaxStages * sizeof(uint64_t) + 64 * sizeof(float);
+  const size_t tail = 2 * kMaxStages * sizeof(uint64_t) + (64 + 64 * 4) * sizeof(float);
   const size_t budget = (g_gemv_ctas_per_sm >= 2 ? 112 : 224) * 1024;
   while (stages > 2 && (size_t)stages * kCW * kc * 2 + x_bytes + tail > budget) --stages;
   while (kc > 256 && (size_t)stages * kCW * kc * 2 + x_bytes + tail > budget) kc -= 256;
@@ -346,6 +417,7 @@ static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
   const int max_useful = (a.M + rpg - 1) / rpg;
   if (grid > max_useful) grid = max_useful;
   if (grid < 1) grid = 1;
+  if (a.epi == 2 && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
   return launch(kern, dim3(grid), dim3(kConsumerThreads + 32), smem, stream, true, a);
 }
 
@@ -409,7 +481,7 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
   using namespace pk;
   if (!g || g->M <= 0 || g->K <= 0) return -1;
   if (!gemv_stream_supported(g->W, g->X, g->N, g->K)) return -1;
-  if (g->x_mode == 1 && (g->hidden_out == nullptr || g->hidden_out == g->X || g->K > 10240)) return -1;
+  if (g->x_mode >= 1 && (g->hidden_out == nullptr || g->hidden_out == g->X || g->K > 10240)) return -1;
   GemvArgs a{};
   a.W = (const bf16*)g->W;
   a.X = (const bf16*)g->X;
@@ -430,6 +502,12 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
   a.hidden_out = (bf16*)g->hidden_out;
   a.normed_out = (bf16*)g->normed_out;
   a.epi = g->epi;
+  if (g->x_mode == 2 || g->epi == 2) {
+    const pk_tp_comm* comm = static_cast<const pk_tp_comm*>(g->tp_comm);
+    if (!comm) return -1;
+    if ((int64_t)g->N * (g->epi == 2 ? g->M : g->K) * 2 > comm->d.slot_bytes) return -2;
+    a.tp = comm->d;
+  }
   return (int)launch_gemv(a, g->N, stream);
 }
 

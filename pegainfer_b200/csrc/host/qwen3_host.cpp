@@ -31,7 +31,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_REQ(batch_prefill_cta_tile_q_with_override) PQ_REQ(batch_prefill_paged_cuda_with_cta_tile_q)
   PQ_REQ(paged_attention_decode_cuda) PQ_REQ(paged_attention_decode_split_kv_cuda)
   PQ_REQ(flashinfer_top1_cuda)
-  PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused)
+  PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused) PQ_OPT(pk_b200_gemm_segments)
   PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
 #undef PQ_REQ
@@ -563,9 +563,17 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   for (int li = 0; li < c.num_hidden_layers; ++li) {  // forward_layer_batch_paged (prefill.rs:73-188)
     TransformerBlock& L = layers[li];
     k.rms_norm_batched_cuda(hcur, L.input_layernorm.data.bf(), nrm.data.bf(), H, T, eps, st);
-    gemm_rows_into(L.attention.qkv_proj, 0, qd, nrm.data.bf(), T, qb.data.bf());
-    gemm_rows_into(L.attention.qkv_proj, qd, kd, nrm.data.bf(), T, kb.data.bf());
-    gemm_rows_into(L.attention.qkv_proj, qd + kd, kd, nrm.data.bf(), T, vb.data.bf());
+    if (rt.mode >= 1 && k.pk_b200_gemm_segments && T > 1) {
+      // one tensor-core launch over the stacked [q;k;v] weight, three outputs (same arithmetic)
+      pk_bf16* outs[3] = {qb.data.bf(), kb.data.bf(), vb.data.bf()};
+      const int segs[3] = {qd, kd, kd};
+      if (k.pk_b200_gemm_segments(L.attention.qkv_proj.data.bf(), nrm.data.bf(), outs, segs, qd + 2 * kd, T, H, st) != 0)
+        return fail("pk_b200_gemm_segments failed");
+    } else {
+      gemm_rows_into(L.attention.qkv_proj, 0, qd, nrm.data.bf(), T, qb.data.bf());
+      gemm_rows_into(L.attention.qkv_proj, qd, kd, nrm.data.bf(), T, kb.data.bf());
+      gemm_rows_into(L.attention.qkv_proj, qd + kd, kd, nrm.data.bf(), T, vb.data.bf());
+    }
     // prefill_attention_paged_into (ops/attention.rs:310-458)
     if (n_req == 1)
       k.prefill_qk_norm_rope_only_cuda(qb.data.bf(), kb.data.bf(), L.attention.q_norm.data.bf(),
@@ -694,24 +702,24 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
     g.M = Mrows; g.N = bs; g.K = K;
     g.x_mode = x_mode; g.residual = residual; g.norm_w = nw; g.eps = eps;
     g.hidden_out = hout; g.normed_out = nullptr; g.epi = epi;
+    g.tp_comm = tp_comm;
     if (k.pk_b200_gemv_fused(&g, st) != 0) return fail("pk_b200_gemv_fused rejected its arguments");
     return true;
   };
+  // Tensor parallel: the row-parallel GEMVs (o_proj, down_proj) push their partial rows to every rank
+  // (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches per layer at any TP
+  // degree, the two all-reduces of the layer live inside the GEMVs.
+  const int red_mode = tp_on ? 2 : 1;
+  const int push_epi = tp_on ? 2 : 0;
   const pk_bf16* prev_residual = zero_residual.bf();  // layer 0: hidden + 0
-  if (tp_on) k.rms_norm_batched_cuda(Ha, layers[0].input_layernorm.data.bf(), normed.data.bf(), H, bs, eps, st);
+  int first_mode = 1;
   for (int li = 0; li < c.num_hidden_layers; ++li) {
     TransformerBlock& L = layers[li];
     const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
-    if (!tp_on) {
-      // q|k|v = W_qkv . RMSNorm(Ha + prev_residual); Hb = Ha + prev_residual
-      if (!gemv(L.attention.qkv_proj.data.bf(), Ha, qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(), v.data.bf(), qd, kd,
-                kd, 1, prev_residual, L.input_layernorm.data.bf(), Hb, 0))
-        return false;
-    } else {
-      if (!gemv(L.attention.qkv_proj.data.bf(), normed.data.bf(), qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(),
-                v.data.bf(), qd, kd, kd, 0, nullptr, nullptr, nullptr, 0))
-        return false;
-    }
+    // q|k|v = W_qkv . RMSNorm(Ha + prev_residual); Hb = Ha + prev_residual
+    if (!gemv(L.attention.qkv_proj.data.bf(), Ha, qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(), v.data.bf(), qd, kd,
+              kd, li == 0 ? first_mode : red_mode, prev_residual, L.input_layernorm.data.bf(), Hb, 0))
+      return false;
     if (k.pk_b200_decode_attention_fused(
             q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
             M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
@@ -720,41 +728,20 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
             layout.page_stride, sm_scale, st) != 0)
       return fail("pk_b200_decode_attention_fused failed");
     if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0, 0,
-              nullptr, nullptr, nullptr, 0))
+              nullptr, nullptr, nullptr, push_epi))
       return false;
-    if (!tp_on) {
-      // act = SwiGLU(W_gate_up . RMSNorm(Hb + attn_proj)); Ha = Hb + attn_proj
-      if (!gemv(L.mlp.gate_up_proj.data.bf(), Hb, I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, 1,
-                attn_proj.data.bf(), L.post_attention_layernorm.data.bf(), Ha, 1))
-        return false;
-    } else {
-      if (k.pk_tp_all_reduce_add_rms_norm(tp_comm, Ha, attn_proj.data.bf(), L.post_attention_layernorm.data.bf(),
-                                          normed.data.bf(), H, bs, eps, st) != 0)
-        return fail("pk_tp_all_reduce_add_rms_norm failed");
-      if (!gemv(L.mlp.gate_up_proj.data.bf(), normed.data.bf(), I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, 0,
-                nullptr, nullptr, nullptr, 1))
-        return false;
-    }
+    // act = SwiGLU(W_gate_up . RMSNorm(Hb + attn_proj)); Ha = Hb + attn_proj
+    if (!gemv(L.mlp.gate_up_proj.data.bf(), Hb, I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, red_mode,
+              attn_proj.data.bf(), L.post_attention_layernorm.data.bf(), Ha, 1))
+      return false;
     if (!gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), nullptr, nullptr, H, 0, 0, 0,
-              nullptr, nullptr, nullptr, 0))
+              nullptr, nullptr, nullptr, push_epi))
       return false;
-    if (tp_on) {
-      const DeviceVec& nw = li + 1 < c.num_hidden_layers ? layers[li + 1].input_layernorm : norm;
-      if (k.pk_tp_all_reduce_add_rms_norm(tp_comm, Ha, mlp_out.data.bf(), nw.data.bf(), normed.data.bf(), H, bs, eps,
-                                          st) != 0)
-        return fail("pk_tp_all_reduce_add_rms_norm failed");
-    }
     prev_residual = mlp_out.data.bf();
   }
-  if (!tp_on) {
-    if (!gemv(output_projection().data.bf(), Ha, c.vocab_size, H, logits.data.bf(), nullptr, nullptr, c.vocab_size, 0,
-              0, 1, prev_residual, norm.data.bf(), Hb, 0))
-      return false;
-  } else {
-    if (!gemv(output_projection().data.bf(), normed.data.bf(), c.vocab_size, H, logits.data.bf(), nullptr, nullptr,
-              c.vocab_size, 0, 0, 0, nullptr, nullptr, nullptr, 0))
-      return false;
-  }
+  if (!gemv(output_projection().data.bf(), Ha, c.vocab_size, H, logits.data.bf(), nullptr, nullptr, c.vocab_size, 0,
+            0, red_mode, prev_residual, norm.data.bf(), Hb, 0))
+    return false;
   // greedy token for every request inside the same graph
   for (int b = 0; b < bs; ++b)
     k.flashinfer_top1_cuda(logits.data.bf() + (size_t)b * c.vocab_size, static_cast<pk_bf16*>(top1_val.ptr) + b,

@@ -40,7 +40,7 @@ struct KernelLib {
   PQ_FN(paged_attention_decode_cuda) PQ_FN(paged_attention_decode_split_kv_cuda)
   PQ_FN(flashinfer_top1_cuda)
   // B200 extensions (null when driving the reference's kernels)
-  PQ_FN(pk_b200_launch_count) PQ_FN(pk_b200_set_pdl) PQ_FN(pk_b200_gemv_fused)
+  PQ_FN(pk_b200_launch_count) PQ_FN(pk_b200_set_pdl) PQ_FN(pk_b200_gemv_fused) PQ_FN(pk_b200_gemm_segments)
   PQ_FN(pk_b200_decode_attention_fused) PQ_FN(pk_b200_decode_step_persistent) PQ_FN(pk_tp_all_reduce_rows)
   PQ_FN(pk_tp_all_reduce_add_rms_norm) PQ_FN(pk_tp_max_rows)
 #undef PQ_FN

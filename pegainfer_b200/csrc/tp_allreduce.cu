@@ -18,17 +18,6 @@
 
 namespace pk {
 
-constexpr int kTpMaxWorld = 8;
-constexpr int kTpMaxCtas = 64;
-constexpr int kTpThreads = 512;
-
-struct TpDev {
-  uint8_t* stage[kTpMaxWorld];   // stage[p]: rank p's staging base as mapped in THIS process
-  uint32_t* flags[kTpMaxWorld];  // flags[p]: rank p's flag array  [2][kTpMaxCtas][world] + ctl
-  int rank, world;
-  int64_t slot_bytes;            // bytes per (slot, src) region
-};
-
 struct TpArgs {
   TpDev d;
   const bf16* partial;  // this rank's partial [T, dim]
@@ -38,15 +27,6 @@ struct TpArgs {
   int dim, T, mode;
   float eps;
 };
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a) {
   extern __shared__ float tp_row[];  // mode 1: dim floats + 40
@@ -155,10 +135,6 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
 
 }  // namespace pk
 
-struct pk_tp_comm {
-  pk::TpDev d;
-  int64_t staging_bytes;
-};
 
 using namespace pk;
 

@@ -19,7 +19,7 @@ class GemvArgs(C.Structure):
     """pk_b200_gemv_args (include/pegainfer_kernels.h)."""
     _fields_ = [("W", vp), ("X", vp), ("Y", vp * 3), ("seg_rows", i32 * 3), ("M", i32), ("N", i32),
                 ("K", i32), ("x_mode", i32), ("residual", vp), ("norm_w", vp), ("eps", f32),
-                ("hidden_out", vp), ("normed_out", vp), ("epi", i32)]
+                ("hidden_out", vp), ("normed_out", vp), ("epi", i32), ("tp_comm", vp)]
 
 
 # name -> (restype, argtypes); order follows include/pegainfer_kernels.h
@@ -60,6 +60,7 @@ EXT_SIGNATURES = {
     "pk_b200_version": (C.c_char_p, []),
     "pk_b200_launch_count": (i64, [i32]),
     "pk_b200_set_pdl": (None, [i32]),
+    "pk_b200_gemm_segments": (i32, [vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
     "pk_b200_gemv_fused": (i32, [C.POINTER(GemvArgs), vp]),
     "pk_b200_set_gemv_tuning": (None, [i32, i32, i32]),
     "pk_b200_decode_step_persistent": (i32, [vp, vp]),
