@@ -15,6 +15,9 @@
 // coalesced), the GQA group's q heads held in registers so each K/V row is read once for all of
 // them; 8 rows of K and 8 of V are in flight per lane-group per iteration.  The grid is sized so
 // chunks x kv heads x requests covers the 148 SMs; the last CTA of a (request, kv head) merges.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace pk {
@@ -468,6 +471,28 @@ static int pick_max_chunks(int bs, int nkv, int nq, size_t scratch_floats) {
   return mc;
 }
 
+// decode_attention_cluster.cu
+struct ClusterAttnArgs {
+  const bf16 *q, *k_new, *v_new;
+  bf16* out;
+  bf16* kv;
+  int64_t k_off, v_off, stride_page;
+  const int *page_indices, *page_indptr, *last_page_len, *positions;
+  const bf16 *qw, *kw, *cosc, *sinc;
+  float eps, sm_scale_log2;
+  int nq, nkv;
+};
+cudaError_t launch_decode_attention_cluster(const ClusterAttnArgs& a, int nkv, int bs, cudaStream_t stream);
+
+static bool use_cluster_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_ATTN");
+    v = (e && strcmp(e, "ticket") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace pk
 
 using namespace pk;
@@ -543,6 +568,19 @@ int pk_b200_decode_attention_fused(
     int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream) {
   if (head_dim != HD || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0) return -1;
   if (batch_size <= 0) return 0;
+  if (num_qo_heads == 4 * num_kv_heads && page_size == 16 && use_cluster_attention()) {
+    // default: one 8-CTA cluster per (request, kv head), merge over distributed shared memory
+    ClusterAttnArgs c{};
+    c.q = (const bf16*)q; c.k_new = (const bf16*)k; c.v_new = (const bf16*)v; c.out = (bf16*)output;
+    c.kv = (bf16*)kv_data; c.k_off = k_offset_elems; c.v_off = v_offset_elems; c.stride_page = stride_page;
+    c.page_indices = page_indices; c.page_indptr = page_indptr; c.last_page_len = last_page_len_d;
+    c.positions = positions;
+    c.qw = (const bf16*)q_norm_weight; c.kw = (const bf16*)k_norm_weight;
+    c.cosc = (const bf16*)cos_cache; c.sinc = (const bf16*)sin_cache;
+    c.eps = rms_eps; c.sm_scale_log2 = sm_scale * 1.44269504088896340736f;
+    c.nq = num_qo_heads; c.nkv = num_kv_heads;
+    return (int)launch_decode_attention_cluster(c, num_kv_heads, batch_size, stream);
+  }
   DecodeAttnArgs a{};
   a.q = (const bf16*)q; a.out = (bf16*)output; a.kv = (bf16*)kv_data;
   a.k_off = k_offset_elems; a.v_off = v_offset_elems;
