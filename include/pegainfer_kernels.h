@@ -160,6 +160,14 @@ void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
                           uint8_t* row_states_scratch, int* output, int vocab_size,
                           pk_stream stream);
 
+/* Non-greedy sampling: ffi.rs:110-120; csrc/flashinfer_sampling.cu:13-110.  probs = softmax(logits *
+ * inv_temperature) (fp32, written to probs_scratch[vocab]); joint top-k / top-p filtering; multinomial draw
+ * from the renormalised eligible set.  Distribution as the reference; the random stream is splitmix64(seed),
+ * not FlashInfer's Philox.  valid_scratch[0] is set to 1. */
+void gpu_sample_flashinfer_cuda(const pk_bf16* logits, float* probs_scratch, uint8_t* valid_scratch,
+                                int* output, int vocab_size, float inv_temperature, int top_k, float top_p,
+                                uint64_t seed, pk_stream stream);
+
 /* =============================== B200 extensions ===============================
  * Not in ffi.rs.  The fused decode layer used by the host mirror
  * (pegainfer_b200/csrc/host) and the TP hook north_star asks pegainfer-comm to gain. */

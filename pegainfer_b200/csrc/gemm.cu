@@ -143,7 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   // Output features [0,e0) go to Y (row length e0), [e0,e1) to Y1, [e1,M) to Y2: the fused q|k|v
   // projection writes three HiddenStates buffers from one launch (e0 == e1 == M: plain GEMM).
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // power of two >= 2 accumulator stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -350,13 +350,30 @@ void launch_gemm_seg(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
   const bool tma_ok = K % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(X) & 15) == 0;
   if (tma_ok && gemm_impl_mode() == 0) {
+    // Tile width by wave count: tiles = ceil(N/128) * ceil(M/BN) on `sms` persistent CTAs; cost ~ waves * (BN + c).
+    // M = 2560 outputs (o_proj / down_proj of Qwen3-4B) at 2048 tokens: BN 256 -> 160 tiles = 2 waves of 256-wide
+    // tiles, BN 160 -> 256 tiles = 2 waves of 160-wide tiles (profiles/README.md, r1 v3: tile quantisation).
     const int m_tiles = (N + BM - 1) / BM;
-    const bool small = m_tiles * ((M + 255) / 256) < sm_count();
-    const int bn = small ? 128 : 256;
+    const int sms = sm_count();
+    int best_bn = 256;
+    long best_cost = -1;
+    const int cands[3] = {256, 160, 128};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int bnc = cands[ci];
+      const long tiles = (long)m_tiles * ((M + bnc - 1) / bnc);
+      const long waves = (tiles + sms - 1) / sms;
+      const long cost = waves * (bnc + 32);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_bn = bnc;
+      }
+    }
     CUtensorMap mx, mw;
-    if (make_map(&mx, X, N, K, BM) && make_map(&mw, W, M, K, bn)) {
-      if (small)
+    if (make_map(&mx, X, N, K, BM) && make_map(&mw, W, M, K, best_bn)) {
+      if (best_bn == 128)
         launch_tc<128, 6>(mx, mw, Y, Y1, Y2, e0, e1, M, N, K, stream);
+      else if (best_bn == 160)
+        launch_tc<160, 5>(mx, mw, Y, Y1, Y2, e0, e1, M, N, K, stream);
       else
         launch_tc<256, 4>(mx, mw, Y, Y1, Y2, e0, e1, M, N, K, stream);
       return;

@@ -133,3 +133,164 @@ void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Non-greedy sampling: temperature softmax + top-k / top-p filtering + multinomial draw.
+// Replaces csrc/flashinfer_sampling.cu:13-110 (logits_to_probs_kernel + FlashInfer
+// {TopKTopP,TopK,TopP,}SamplingFromProb).  Distribution semantics are the reference's: probs =
+// softmax(bf16 logits * inv_temperature) in fp32; a token is eligible iff it is among the top_k most probable
+// (top_k > 0) AND inside the smallest prefix of the probability-sorted vocabulary whose mass reaches top_p
+// (top_p < 1), both evaluated on the unfiltered probs ("joint" filtering); the draw is from the renormalised
+// eligible set.  The RANDOM STREAM is not FlashInfer's Philox: u = splitmix64(seed) (documented in DESIGN.md);
+// the reference's own test only pins greedy-equivalent cases and "token in range" (ops/tests.rs:228-305).
+// One CTA; thresholds by bisection on the fp32 bit pattern (probabilities are >= 0, so bits are monotone).
+namespace pk {
+
+constexpr int kSampleThreads = 1024;
+
+__device__ __forceinline__ float block_reduce_sum_f(float v, float* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  float t = threadIdx.x < 32 ? sm[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (lane == 0) sm[32] = t;
+  }
+  __syncthreads();
+  return sm[32];
+}
+__device__ __forceinline__ float block_reduce_max_f(float v, float* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  float t = threadIdx.x < 32 ? sm[threadIdx.x] : -INFINITY;
+  if (w == 0) {
+    t = warp_max(t);
+    if (lane == 0) sm[32] = t;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const bf16* __restrict__ logits, float* __restrict__ probs,
+                                                                uint8_t* __restrict__ valid, int* __restrict__ out, int n,
+                                                                float inv_temperature, int top_k, float top_p,
+                                                                uint64_t seed) {
+  __shared__ float sm[40];
+  __shared__ float s_scan[kSampleThreads];
+  __shared__ int s_pick;
+  const int tid = threadIdx.x;
+  pdl_wait();
+  // ---- softmax(logits * inv_temperature), fp32 (logits_to_probs_kernel) ----
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += kSampleThreads) {
+    const float v = bf2f(logits[i]) * inv_temperature;
+    probs[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_reduce_max_f(mx, sm);
+  float sum = 0.f;
+  for (int i = tid; i < n; i += kSampleThreads) {
+    const float v = expf(probs[i] - mx);
+    probs[i] = v;
+    sum += v;
+  }
+  sum = block_reduce_sum_f(sum, sm);
+  const float inv = 1.0f / sum;
+  for (int i = tid; i < n; i += kSampleThreads) probs[i] *= inv;
+  __syncthreads();
+  // ---- eligibility threshold: largest t with count(p >= t) >= top_k and mass(p >= t) >= top_p ----
+  uint32_t thr_bits = 0;  // p >= +0 : everything
+  if (top_k > 0 && top_k < n) {
+    uint32_t lo = 0, hi = 0x3f800001u;  // invariant: count(p >= lo) >= k, count(p >= hi) < k
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      float c = 0.f;
+      for (int i = tid; i < n; i += kSampleThreads) c += (__float_as_uint(probs[i]) >= mid) ? 1.f : 0.f;
+      c = block_reduce_sum_f(c, sm);
+      if (c >= (float)top_k) lo = mid; else hi = mid;
+    }
+    thr_bits = lo;
+  }
+  if (top_p < 1.0f) {
+    uint32_t lo = 0, hi = 0x3f800001u;  // invariant: mass(p >= lo) >= top_p, mass(p >= hi) < top_p
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      float msum = 0.f;
+      for (int i = tid; i < n; i += kSampleThreads) {
+        const float pv = probs[i];
+        msum += (__float_as_uint(pv) >= mid) ? pv : 0.f;
+      }
+      msum = block_reduce_sum_f(msum, sm);
+      if (msum >= top_p) lo = mid; else hi = mid;
+    }
+    thr_bits = max(thr_bits, lo);
+  }
+  // ---- draw from the renormalised eligible set by inverse CDF in index order ----
+  float total = 0.f;
+  for (int i = tid; i < n; i += kSampleThreads) {
+    const float pv = probs[i];
+    total += (__float_as_uint(pv) >= thr_bits) ? pv : 0.f;
+  }
+  total = block_reduce_sum_f(total, sm);
+  const float u = (float)(splitmix64(seed) >> 40) * (1.0f / 16777216.0f) * total;
+  if (tid == 0) s_pick = -1;
+  float running = 0.f;
+  int last_ok = -1;
+  for (int base = 0; base < n; base += kSampleThreads) {
+    const int i = base + tid;
+    const float pv = (i < n && __float_as_uint(probs[i]) >= thr_bits) ? probs[i] : 0.f;
+    if (pv > 0.f) last_ok = i;
+    // inclusive block scan (Hillis-Steele over shared memory)
+    s_scan[tid] = pv;
+    __syncthreads();
+    for (int off = 1; off < kSampleThreads; off <<= 1) {
+      const float add = tid >= off ? s_scan[tid - off] : 0.f;
+      __syncthreads();
+      s_scan[tid] += add;
+      __syncthreads();
+    }
+    const float incl = running + s_scan[tid];
+    if (pv > 0.f && incl > u && incl - pv <= u) atomicMax(&s_pick, -1), atomicCAS(&s_pick, -1, i);
+    running += s_scan[kSampleThreads - 1];
+    __syncthreads();
+    if (s_pick >= 0) break;
+  }
+  // rounding at the very end of the CDF: fall back to the last eligible token
+  int lo_all = last_ok;
+  for (int o = 16; o > 0; o >>= 1) lo_all = max(lo_all, __shfl_xor_sync(0xffffffffu, lo_all, o));
+  __shared__ int s_last[32];
+  if ((tid & 31) == 0) s_last[tid >> 5] = lo_all;
+  __syncthreads();
+  if (tid == 0) {
+    int pick = s_pick;
+    if (pick < 0) {
+      for (int w = 0; w < kSampleThreads / 32; ++w) pick = max(pick, s_last[w]);
+      if (pick < 0) pick = 0;
+    }
+    out[0] = pick;
+    if (valid) valid[0] = 1;
+  }
+}
+
+}  // namespace pk
+
+extern "C" void gpu_sample_flashinfer_cuda(const pk_bf16* logits, float* probs_scratch, uint8_t* valid_scratch,
+                                           int* output, int vocab_size, float inv_temperature, int top_k,
+                                           float top_p, uint64_t seed, pk_stream stream) {
+  if (vocab_size <= 0) return;
+  pk::launch(pk::sample_kernel, dim3(1), dim3(pk::kSampleThreads), 0, stream, true, (const pk::bf16*)logits,
+             probs_scratch, valid_scratch, output, vocab_size, inv_temperature, top_k, top_p, seed);
+}

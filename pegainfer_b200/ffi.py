@@ -53,6 +53,7 @@ SIGNATURES = {
     "paged_attention_decode_split_kv_cuda": (i32, [vp, vp, vp, i64, i64] + [vp] * 10 + [i32] * 6 + [i64, f32, vp]),
     "argmax_cuda": (None, [vp, vp, i32, vp]),
     "flashinfer_top1_cuda": (None, [vp, vp, vp, vp, i32, vp]),
+    "gpu_sample_flashinfer_cuda": (None, [vp, vp, vp, vp, i32, f32, i32, f32, C.c_uint64, vp]),
 }
 
 # B200 extensions (absent from the reference's library)

