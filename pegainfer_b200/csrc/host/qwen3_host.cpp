@@ -706,42 +706,88 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
     if (k.pk_b200_gemv_fused(&g, st) != 0) return fail("pk_b200_gemv_fused rejected its arguments");
     return true;
   };
-  // Tensor parallel: the row-parallel GEMVs (o_proj, down_proj) push their partial rows to every rank
-  // (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches per layer at any TP
-  // degree, the two all-reduces of the layer live inside the GEMVs.
+  // Tensor parallel, two variants (both custom kernels over NVLink peer memory, no NCCL on the data path):
+  //  * fused (default for world <= 2; PK_TP_FUSED=1): the row-parallel GEMVs (o_proj, down_proj) push their
+  //    partial rows to every rank (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches
+  //    per layer, the layer's two all-reduces live inside the GEMVs.
+  //  * kernel (default for world >= 4; PK_TP_FUSED=0): one-shot all-reduce kernel fused with add + RMSNorm between
+  //    the GEMVs (7 launches per layer).  Measured on 8 x B200 (Qwen3-8B, bs 1): 411 tok/s vs 350 tok/s for the
+  //    fused variant -- with 7 peers the per-CTA system-scope fence + grid ticket of the push epilogue costs more
+  //    than a single-CTA collective; at 2 GPUs the fused variant wins (339 vs 323 tok/s).
+  static const int tp_fused_env = [] {
+    const char* e = getenv("PK_TP_FUSED");
+    return e ? atoi(e) : -1;
+  }();
+  const bool tp_fuse = tp_on && (tp_fused_env >= 0 ? tp_fused_env != 0 : tp.world_size <= 2);
   const int red_mode = tp_on ? 2 : 1;
   const int push_epi = tp_on ? 2 : 0;
   const pk_bf16* prev_residual = zero_residual.bf();  // layer 0: hidden + 0
-  int first_mode = 1;
-  for (int li = 0; li < c.num_hidden_layers; ++li) {
-    TransformerBlock& L = layers[li];
-    const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
-    // q|k|v = W_qkv . RMSNorm(Ha + prev_residual); Hb = Ha + prev_residual
-    if (!gemv(L.attention.qkv_proj.data.bf(), Ha, qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(), v.data.bf(), qd, kd,
-              kd, li == 0 ? first_mode : red_mode, prev_residual, L.input_layernorm.data.bf(), Hb, 0))
+  if (tp_on && !tp_fuse) {
+    k.rms_norm_batched_cuda(Ha, layers[0].input_layernorm.data.bf(), normed.data.bf(), H, bs, eps, st);
+    for (int li = 0; li < c.num_hidden_layers; ++li) {
+      TransformerBlock& L = layers[li];
+      const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
+      if (!gemv(L.attention.qkv_proj.data.bf(), normed.data.bf(), qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(),
+                v.data.bf(), qd, kd, kd, 0, nullptr, nullptr, nullptr, 0))
+        return false;
+      if (k.pk_b200_decode_attention_fused(
+              q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
+              M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
+              L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
+              static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize,
+              bs, layout.page_stride, sm_scale, st) != 0)
+        return fail("pk_b200_decode_attention_fused failed");
+      if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0,
+                0, nullptr, nullptr, nullptr, 0))
+        return false;
+      if (k.pk_tp_all_reduce_add_rms_norm(tp_comm, Ha, attn_proj.data.bf(), L.post_attention_layernorm.data.bf(),
+                                          normed.data.bf(), H, bs, eps, st) != 0)
+        return fail("pk_tp_all_reduce_add_rms_norm failed");
+      if (!gemv(L.mlp.gate_up_proj.data.bf(), normed.data.bf(), I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, 0,
+                nullptr, nullptr, nullptr, 1))
+        return false;
+      if (!gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), nullptr, nullptr, H, 0, 0, 0,
+                nullptr, nullptr, nullptr, 0))
+        return false;
+      const DeviceVec& nw = li + 1 < c.num_hidden_layers ? layers[li + 1].input_layernorm : norm;
+      if (k.pk_tp_all_reduce_add_rms_norm(tp_comm, Ha, mlp_out.data.bf(), nw.data.bf(), normed.data.bf(), H, bs, eps,
+                                          st) != 0)
+        return fail("pk_tp_all_reduce_add_rms_norm failed");
+    }
+    if (!gemv(output_projection().data.bf(), normed.data.bf(), c.vocab_size, H, logits.data.bf(), nullptr, nullptr,
+              c.vocab_size, 0, 0, 0, nullptr, nullptr, nullptr, 0))
       return false;
-    if (k.pk_b200_decode_attention_fused(
-            q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
-            M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
-            L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
-            static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize, bs,
-            layout.page_stride, sm_scale, st) != 0)
-      return fail("pk_b200_decode_attention_fused failed");
-    if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0, 0,
-              nullptr, nullptr, nullptr, push_epi))
+  } else {
+    for (int li = 0; li < c.num_hidden_layers; ++li) {
+      TransformerBlock& L = layers[li];
+      const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
+      // q|k|v = W_qkv . RMSNorm(Ha + prev_residual); Hb = Ha + prev_residual
+      if (!gemv(L.attention.qkv_proj.data.bf(), Ha, qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(), v.data.bf(), qd, kd,
+                kd, li == 0 ? 1 : red_mode, prev_residual, L.input_layernorm.data.bf(), Hb, 0))
+        return false;
+      if (k.pk_b200_decode_attention_fused(
+              q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
+              M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
+              L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
+              static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize,
+              bs, layout.page_stride, sm_scale, st) != 0)
+        return fail("pk_b200_decode_attention_fused failed");
+      if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0,
+                0, nullptr, nullptr, nullptr, push_epi))
+        return false;
+      // act = SwiGLU(W_gate_up . RMSNorm(Hb + attn_proj)); Ha = Hb + attn_proj
+      if (!gemv(L.mlp.gate_up_proj.data.bf(), Hb, I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, red_mode,
+                attn_proj.data.bf(), L.post_attention_layernorm.data.bf(), Ha, 1))
+        return false;
+      if (!gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), nullptr, nullptr, H, 0, 0, 0,
+                nullptr, nullptr, nullptr, push_epi))
+        return false;
+      prev_residual = mlp_out.data.bf();
+    }
+    if (!gemv(output_projection().data.bf(), Ha, c.vocab_size, H, logits.data.bf(), nullptr, nullptr, c.vocab_size, 0,
+              0, red_mode, prev_residual, norm.data.bf(), Hb, 0))
       return false;
-    // act = SwiGLU(W_gate_up . RMSNorm(Hb + attn_proj)); Ha = Hb + attn_proj
-    if (!gemv(L.mlp.gate_up_proj.data.bf(), Hb, I, H, mlp_act.data.bf(), nullptr, nullptr, I, 0, 0, red_mode,
-              attn_proj.data.bf(), L.post_attention_layernorm.data.bf(), Ha, 1))
-      return false;
-    if (!gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), nullptr, nullptr, H, 0, 0, 0,
-              nullptr, nullptr, nullptr, push_epi))
-      return false;
-    prev_residual = mlp_out.data.bf();
   }
-  if (!gemv(output_projection().data.bf(), Ha, c.vocab_size, H, logits.data.bf(), nullptr, nullptr, c.vocab_size, 0,
-            0, red_mode, prev_residual, norm.data.bf(), Hb, 0))
-    return false;
   // greedy token for every request inside the same graph
   for (int b = 0; b < bs; ++b)
     k.flashinfer_top1_cuda(logits.data.bf() + (size_t)b * c.vocab_size, static_cast<pk_bf16*>(top1_val.ptr) + b,
