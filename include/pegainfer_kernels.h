@@ -265,6 +265,42 @@ int pk_b200_decode_attention_fused(
     int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
     int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream);
 
+/* Causal GQA prefill attention over the paged cache on tcgen05/TMEM (prefill_attention_tc.cu): the kernel behind
+ * batch_prefill_paged_cuda* when PK_PREFILL_ATTN=tc, callable directly.  Same inputs as the ABI entry minus the
+ * FlashInfer tile plan (tiles are derived from q_indptr on the device).  v_desc_mode: 0 (bring-up switch for the
+ * MN-major V descriptor, see the source).  Returns 0 / cudaError / -1 for unsupported shapes (head_dim != 128). */
+int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
+                                 int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
+                                 const int* last_page_len_d, const int* q_indptr, int num_qo_heads, int num_kv_heads,
+                                 int head_dim, int page_size, int seq_len, int batch_size, int64_t stride_page,
+                                 float sm_scale, int v_desc_mode, pk_stream stream);
+
+/* pk_b200_decode_attention_fused plus an L2 prefetch of weights that FOLLOWING launches will stream.
+ * bs-1 decode attention is latency-bound (a few MB of K/V against ~10 us of dependent steps) and leaves HBM
+ * idle; extra clusters of the same launch use that window to pull weight rows into the 126 MB L2
+ * (cp.async.bulk.prefetch.L2), after the previous kernel has drained.  A span describes one row-major weight
+ * block and how the GEMV that will read it cuts it: `slices` = that GEMV's grid (pk_b200_gemv_grid), and the
+ * first `prefetch_rows` rows of every slice are requested so all of its CTAs gain equally.  Results are
+ * identical with or without spans.  At most 4 spans; row_bytes % 16 == 0, base 16-byte aligned (else -1). */
+typedef struct pk_b200_prefetch_span {
+  const void* base;      /* first row of the weight block */
+  int32_t rows;          /* rows of the block (= the GEMV's M for that block) */
+  int32_t row_bytes;     /* K * 2 */
+  int32_t slices;        /* grid of the GEMV that will read it */
+  int32_t prefetch_rows; /* leading rows of each slice to request */
+} pk_b200_prefetch_span;
+int pk_b200_decode_attention_fused_prefetch(
+    const pk_bf16* q, const pk_bf16* k, const pk_bf16* v, pk_bf16* output, pk_bf16* kv_data,
+    int64_t k_offset_elems, int64_t v_offset_elems, const int* page_indices,
+    const int* page_indptr, const int* last_page_len_d, const int* positions,
+    const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+    const pk_bf16* sin_cache, float rms_eps, float* partial_scratch, int* counters,
+    int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
+    int page_size, int batch_size, int64_t stride_page, float sm_scale,
+    const pk_b200_prefetch_span* spans, int num_spans, pk_stream stream);
+/* Grid (row slices) pk_b200_gemv_fused / gemm_cuda(N <= 4) uses for M output rows with epilogue `epi`. */
+int pk_b200_gemv_grid(int M, int epi);
+
 /* ---- TP all-reduce hook (pegainfer-qwen3-4b/src/weights.rs:396-405) ----------
  * One-shot all-reduce over NVLink peer memory: every rank owns a symmetric staging
  * buffer; peers' buffers are mapped (cudaIpc / peer access).  In-place SUM over

@@ -148,6 +148,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
       : "memory");
 }
 
+// fire-and-forget L2 prefetch of a contiguous global range; bytes % 16 == 0, address 16-B aligned
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---- tensor-parallel peer-memory communicator (tp_allreduce.cu, gemv.cu) ----
 constexpr int kTpMaxWorld = 8;
 constexpr int kTpMaxCtas = 64;

@@ -18,7 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
+#include "decode_attention_cluster.cuh"
 
 namespace pk {
 
@@ -471,18 +471,6 @@ static int pick_max_chunks(int bs, int nkv, int nq, size_t scratch_floats) {
   return mc;
 }
 
-// decode_attention_cluster.cu
-struct ClusterAttnArgs {
-  const bf16 *q, *k_new, *v_new;
-  bf16* out;
-  bf16* kv;
-  int64_t k_off, v_off, stride_page;
-  const int *page_indices, *page_indptr, *last_page_len, *positions;
-  const bf16 *qw, *kw, *cosc, *sinc;
-  float eps, sm_scale_log2;
-  int nq, nkv;
-};
-cudaError_t launch_decode_attention_cluster(const ClusterAttnArgs& a, int nkv, int bs, cudaStream_t stream);
 
 static bool use_cluster_attention() {
   static int v = -1;
@@ -491,6 +479,18 @@ static bool use_cluster_attention() {
     v = (e && strcmp(e, "ticket") == 0) ? 0 : 1;
   }
   return v == 1;
+}
+
+// Extra cluster rows of the fused launch that only issue L2 prefetches (PK_PF_Y, default 8 -> 64 CTAs).
+static int prefetch_cluster_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_PF_Y");
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+    if (v > 32) v = 32;
+  }
+  return v;
 }
 
 }  // namespace pk
@@ -558,14 +558,15 @@ int paged_attention_decode_split_kv_cuda(
                      num_qo_heads);
 }
 
-int pk_b200_decode_attention_fused(
+static int decode_attention_fused_impl(
     const pk_bf16* q, const pk_bf16* k, const pk_bf16* v, pk_bf16* output, pk_bf16* kv_data,
     int64_t k_offset_elems, int64_t v_offset_elems, const int* page_indices,
     const int* page_indptr, const int* last_page_len_d, const int* positions,
     const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
     const pk_bf16* sin_cache, float rms_eps, float* partial_scratch, int* counters,
     int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
-    int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream) {
+    int page_size, int batch_size, int64_t stride_page, float sm_scale,
+    const pk_b200_prefetch_span* spans, int num_spans, pk_stream stream) {
   if (head_dim != HD || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0) return -1;
   if (batch_size <= 0) return 0;
   if (num_qo_heads == 4 * num_kv_heads && page_size == 16 && use_cluster_attention()) {
@@ -579,6 +580,13 @@ int pk_b200_decode_attention_fused(
     c.cosc = (const bf16*)cos_cache; c.sinc = (const bf16*)sin_cache;
     c.eps = rms_eps; c.sm_scale_log2 = sm_scale * 1.44269504088896340736f;
     c.nq = num_qo_heads; c.nkv = num_kv_heads;
+    for (int s = 0; s < num_spans && c.npf < kMaxPfSpans; ++s) {
+      const pk_b200_prefetch_span& sp = spans[s];
+      if (!sp.base || sp.rows <= 0 || sp.slices <= 0 || sp.prefetch_rows <= 0) continue;
+      if (sp.row_bytes <= 0 || sp.row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(sp.base) & 15) != 0) return -1;
+      c.pf[c.npf++] = PfSpan{static_cast<const uint8_t*>(sp.base), sp.rows, sp.row_bytes, sp.slices, sp.prefetch_rows};
+    }
+    c.pf_y = prefetch_cluster_rows();
     return (int)launch_decode_attention_cluster(c, num_kv_heads, batch_size, stream);
   }
   DecodeAttnArgs a{};
@@ -596,6 +604,38 @@ int pk_b200_decode_attention_fused(
   a.qw = (const bf16*)q_norm_weight; a.kw = (const bf16*)k_norm_weight;
   a.cosc = (const bf16*)cos_cache; a.sinc = (const bf16*)sin_cache; a.eps = rms_eps;
   return (int)launch_decode_attn(a, dim3(a.max_chunks, num_kv_heads, batch_size), stream);
+}
+
+int pk_b200_decode_attention_fused(
+    const pk_bf16* q, const pk_bf16* k, const pk_bf16* v, pk_bf16* output, pk_bf16* kv_data,
+    int64_t k_offset_elems, int64_t v_offset_elems, const int* page_indices,
+    const int* page_indptr, const int* last_page_len_d, const int* positions,
+    const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+    const pk_bf16* sin_cache, float rms_eps, float* partial_scratch, int* counters,
+    int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
+    int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream) {
+  return decode_attention_fused_impl(q, k, v, output, kv_data, k_offset_elems, v_offset_elems, page_indices,
+                                     page_indptr, last_page_len_d, positions, q_norm_weight, k_norm_weight,
+                                     cos_cache, sin_cache, rms_eps, partial_scratch, counters, chunk_tokens,
+                                     max_chunks, num_qo_heads, num_kv_heads, head_dim, page_size, batch_size,
+                                     stride_page, sm_scale, nullptr, 0, stream);
+}
+
+int pk_b200_decode_attention_fused_prefetch(
+    const pk_bf16* q, const pk_bf16* k, const pk_bf16* v, pk_bf16* output, pk_bf16* kv_data,
+    int64_t k_offset_elems, int64_t v_offset_elems, const int* page_indices,
+    const int* page_indptr, const int* last_page_len_d, const int* positions,
+    const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+    const pk_bf16* sin_cache, float rms_eps, float* partial_scratch, int* counters,
+    int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
+    int page_size, int batch_size, int64_t stride_page, float sm_scale,
+    const pk_b200_prefetch_span* spans, int num_spans, pk_stream stream) {
+  if (num_spans < 0 || (num_spans > 0 && !spans)) return -1;
+  return decode_attention_fused_impl(q, k, v, output, kv_data, k_offset_elems, v_offset_elems, page_indices,
+                                     page_indptr, last_page_len_d, positions, q_norm_weight, k_norm_weight,
+                                     cos_cache, sin_cache, rms_eps, partial_scratch, counters, chunk_tokens,
+                                     max_chunks, num_qo_heads, num_kv_heads, head_dim, page_size, batch_size,
+                                     stride_page, sm_scale, spans, num_spans, stream);
 }
 
 }  // extern "C"

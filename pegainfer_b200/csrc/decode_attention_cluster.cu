@@ -10,7 +10,7 @@
 // is 3-4 dependent global round trips) there is no global-memory synchronisation at all.
 // The CTA that owns the step's position also appends the normed/roped K and the V row to the paged cache and
 // injects the new token from shared memory.  Arithmetic and rounding points: see decode_attention.cu.
-#include "common.cuh"
+#include "decode_attention_cluster.cuh"
 
 namespace pk {
 
@@ -22,17 +22,6 @@ constexpr int C_U = 4;               // steps per round -> 64 tokens
 constexpr int C_ROUND = C_STEP * C_U;
 constexpr int C_CLUSTER = 8;
 constexpr int C_GROUP = 4;
-
-struct ClusterAttnArgs {
-  const bf16 *q, *k_new, *v_new;
-  bf16* out;
-  bf16* kv;
-  int64_t k_off, v_off, stride_page;
-  const int *page_indices, *page_indptr, *last_page_len, *positions;
-  const bf16 *qw, *kw, *cosc, *sinc;
-  float eps, sm_scale_log2;
-  int nq, nkv;
-};
 
 __device__ __forceinline__ float cex2(float x) {
   float y;
@@ -90,7 +79,10 @@ __device__ __forceinline__ void c_norm_rope(const bf16* __restrict__ src, const 
   reinterpret_cast<uint2*>(dst)[lane] = res;
 }
 
-__global__ void __cluster_dims__(C_CLUSTER, 1, 1) __launch_bounds__(C_THREADS, 1)
+#ifndef PK_ATTN_MIN_CTAS
+#define PK_ATTN_MIN_CTAS 1
+#endif
+__global__ void __cluster_dims__(C_CLUSTER, 1, 1) __launch_bounds__(C_THREADS, PK_ATTN_MIN_CTAS)
 decode_attention_cluster_kernel(const ClusterAttnArgs a) {
   __shared__ __align__(16) float st_o[C_WARPS + 1][C_GROUP][CHD];
   __shared__ float st_m[C_WARPS + 1][C_GROUP], st_d[C_WARPS + 1][C_GROUP];
@@ -100,6 +92,33 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
   __shared__ __align__(16) float c_o[C_CLUSTER][C_GROUP][CHD];
   __shared__ float c_m[C_CLUSTER][C_GROUP], c_d[C_CLUSTER][C_GROUP];
 
+  if ((int)blockIdx.y >= a.nkv) {
+    // ---- prefetch clusters: decode attention is latency-bound and leaves HBM almost idle (a few MB of K/V per
+    // layer against ~10 us of dependent steps), so these CTAs spend the window pulling the head of the NEXT
+    // GEMVs' weight slices into L2 (fire-and-forget bulk prefetches).  They wait for the previous kernel first:
+    // issuing earlier would only compete with the qkv GEMV's own stream.
+    pdl_launch_dependents();
+    pdl_wait();
+    const int ncta = a.pf_y * C_CLUSTER * (int)gridDim.z;
+    const int cta = (((int)blockIdx.z * a.pf_y) + ((int)blockIdx.y - a.nkv)) * C_CLUSTER + (int)blockIdx.x;
+    const int nthr = ncta * C_THREADS;
+    int unit0 = 0;
+    for (int s = 0; s < a.npf; ++s) {
+      const PfSpan sp = a.pf[s];
+      const int units = sp.slices * sp.pf_rows;
+      // round-robin over all prefetch threads, continuing where the previous span stopped
+      int u = cta * C_THREADS + (int)threadIdx.x - unit0 % nthr;
+      if (u < 0) u += nthr;
+      for (; u < units; u += nthr) {
+        const int slice = u / sp.pf_rows, j = u - slice * sp.pf_rows;
+        const int r0 = (int)(((int64_t)slice * sp.rows) / sp.slices);
+        const int r1 = (int)(((int64_t)(slice + 1) * sp.rows) / sp.slices);
+        if (r0 + j < r1) bulk_prefetch_l2(sp.base + (size_t)(r0 + j) * sp.row_bytes, (uint32_t)sp.row_bytes);
+      }
+      unit0 += units;
+    }
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int rank = (int)cluster_rank();
   const int kvh = blockIdx.y, b = blockIdx.z;
@@ -309,7 +328,8 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
 }
 
 cudaError_t launch_decode_attention_cluster(const ClusterAttnArgs& a, int nkv, int bs, cudaStream_t stream) {
-  return launch(decode_attention_cluster_kernel, dim3(C_CLUSTER, nkv, bs), dim3(C_THREADS), 0, stream, true, a);
+  const int pf_y = a.npf > 0 ? a.pf_y : 0;
+  return launch(decode_attention_cluster_kernel, dim3(C_CLUSTER, nkv + pf_y, bs), dim3(C_THREADS), 0, stream, true, a);
 }
 
 }  // namespace pk

@@ -60,8 +60,12 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc)
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+#ifndef PK_GEMV_MIN_CTAS
+#define PK_GEMV_MIN_CTAS 1  // occupancy hint of the streaming kernel (register cap = 64K / (288 * this))
+#endif
+
 template <int NTOK>
-__global__ void __launch_bounds__(kConsumerThreads + 32, 1)
+__global__ void __launch_bounds__(kConsumerThreads + 32, PK_GEMV_MIN_CTAS)
 gemv_stream_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int stages = a.stages;
@@ -392,6 +396,16 @@ bool gemv_stream_supported(const void* W, const void* X, int N, int K) {
   return N >= 1 && N <= 4 && K % 8 == 0 && al16(W) && al16(X) && (size_t)N * K * 2 <= 96 * 1024;
 }
 
+// CTA count of the streaming kernel: every CTA owns >= one row group, at most ctas_per_sm CTAs per SM.
+int gemv_grid(int M, int epi) {
+  gemv_tuning();
+  const int rpg = epi == 1 ? kCW / 2 : kCW;
+  int grid = sm_count() * g_gemv_ctas_per_sm;
+  const int max_useful = (M + rpg - 1) / rpg;
+  if (grid > max_useful) grid = max_useful;
+  return grid < 1 ? 1 : grid;
+}
+
 template <int NTOK>
 static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
   gemv_tuning();
@@ -412,11 +426,7 @@ static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[NTOK] = smem;
   }
-  const int rpg = a.epi == 1 ? kCW / 2 : kCW;
-  int grid = sm_count() * g_gemv_ctas_per_sm;
-  const int max_useful = (a.M + rpg - 1) / rpg;
-  if (grid > max_useful) grid = max_useful;
-  if (grid < 1) grid = 1;
+  const int grid = gemv_grid(a.M, a.epi);
   if (a.epi == 2 && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
   return launch(kern, dim3(grid), dim3(kConsumerThreads + 32), smem, stream, true, a);
 }
@@ -473,6 +483,8 @@ void gemm_graphsafe_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, 
 }
 
 // ring depth (2..12 stages), CTAs per SM and K elements per row segment of the streaming GEMV; 0 keeps a value
+int pk_b200_gemv_grid(int M, int epi) { return M > 0 ? pk::gemv_grid(M, epi) : 0; }
+
 void pk_b200_set_gemv_tuning(int stages, int ctas_per_sm, int segment_elems) {
   pk::gemv_set_tuning(stages, ctas_per_sm, segment_elems);
 }

@@ -34,6 +34,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused) PQ_OPT(pk_b200_gemm_segments)
   PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
+  PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid)
 #undef PQ_REQ
 #undef PQ_OPT
   if (!missing.empty()) return "kernel library " + p + " lacks:" + missing;
@@ -706,6 +707,43 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
     if (k.pk_b200_gemv_fused(&g, st) != 0) return fail("pk_b200_gemv_fused rejected its arguments");
     return true;
   };
+  // Fused attention launch; when the kernel library offers it, the launch also prefetches into L2 the weights the
+  // next two GEMVs will stream (all of o_proj, the leading rows of every gate_up slice): bs-1 attention is
+  // latency-bound and would otherwise leave HBM idle for ~10 us per layer.  PK_PF_O / PK_PF_GU = rows per GEMV
+  // slice to request (0 disables), defaults tuned on B200 (profiles/README.md).
+  static const int pf_o_rows = [] { const char* e = getenv("PK_PF_O"); return e ? atoi(e) : 0; }();
+  static const int pf_gu_rows = [] { const char* e = getenv("PK_PF_GU"); return e ? atoi(e) : 0; }();
+  const bool can_prefetch = k.pk_b200_decode_attention_fused_prefetch && k.pk_b200_gemv_grid && (pf_o_rows > 0 || pf_gu_rows > 0);
+  const int o_slices = can_prefetch ? k.pk_b200_gemv_grid(H, 0) : 1;
+  const int gu_slices = can_prefetch ? k.pk_b200_gemv_grid(I, 1) : 1;
+  auto attention = [&](TransformerBlock& L, int64_t k_off, int64_t v_off) -> bool {
+    if (!can_prefetch) {
+      if (k.pk_b200_decode_attention_fused(
+              q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
+              M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
+              L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
+              static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize,
+              bs, layout.page_stride, sm_scale, st) != 0)
+        return fail("pk_b200_decode_attention_fused failed");
+      return true;
+    }
+    pk_b200_prefetch_span sp[3];
+    int ns = 0;
+    if (pf_o_rows > 0) sp[ns++] = pk_b200_prefetch_span{L.attention.o_proj.data.bf(), H, qd * 2, o_slices, pf_o_rows};
+    if (pf_gu_rows > 0) {
+      const pk_bf16* gu = L.mlp.gate_up_proj.data.bf();
+      sp[ns++] = pk_b200_prefetch_span{gu, I, H * 2, gu_slices, pf_gu_rows};
+      sp[ns++] = pk_b200_prefetch_span{gu + (size_t)I * H, I, H * 2, gu_slices, pf_gu_rows};
+    }
+    if (k.pk_b200_decode_attention_fused_prefetch(
+            q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
+            M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
+            L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
+            static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize, bs,
+            layout.page_stride, sm_scale, sp, ns, st) != 0)
+      return fail("pk_b200_decode_attention_fused_prefetch failed");
+    return true;
+  };
   // Tensor parallel, two variants (both custom kernels over NVLink peer memory, no NCCL on the data path):
   //  * fused (default for world <= 2; PK_TP_FUSED=1): the row-parallel GEMVs (o_proj, down_proj) push their
   //    partial rows to every rank (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches
@@ -730,13 +768,7 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
       if (!gemv(L.attention.qkv_proj.data.bf(), normed.data.bf(), qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(),
                 v.data.bf(), qd, kd, kd, 0, nullptr, nullptr, nullptr, 0))
         return false;
-      if (k.pk_b200_decode_attention_fused(
-              q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
-              M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
-              L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
-              static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize,
-              bs, layout.page_stride, sm_scale, st) != 0)
-        return fail("pk_b200_decode_attention_fused failed");
+      if (!attention(L, k_off, v_off)) return false;
       if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0,
                 0, nullptr, nullptr, nullptr, 0))
         return false;
@@ -765,13 +797,7 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
       if (!gemv(L.attention.qkv_proj.data.bf(), Ha, qd + 2 * kd, H, q.data.bf(), kbuf.data.bf(), v.data.bf(), qd, kd,
                 kd, li == 0 ? 1 : red_mode, prev_residual, L.input_layernorm.data.bf(), Hb, 0))
         return false;
-      if (k.pk_b200_decode_attention_fused(
-              q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
-              M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
-              L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), eps,
-              static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64, attn_max_chunks, nh, nkv, hd, kPageSize,
-              bs, layout.page_stride, sm_scale, st) != 0)
-        return fail("pk_b200_decode_attention_fused failed");
+      if (!attention(L, k_off, v_off)) return false;
       if (!gemv(L.attention.o_proj.data.bf(), attn_out.data.bf(), H, qd, attn_proj.data.bf(), nullptr, nullptr, H, 0, 0,
                 0, nullptr, nullptr, nullptr, push_epi))
         return false;

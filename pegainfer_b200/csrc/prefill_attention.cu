@@ -15,6 +15,9 @@
 //
 // The caller's tile plan (request_indices / qo_tile_indices / kv_tile_indices) is ignored
 // consistently: tiles are derived from q_indptr on the device; results do not depend on tiling.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace pk {
@@ -327,6 +330,30 @@ static int resolve_cta_tile_q(int64_t packed_qo_len, int head_dim, int override_
   return 0;
 }
 
+// prefill_attention_tc.cu
+int launch_prefill_tc(const bf16* q, bf16* out, const bf16* k_base, const bf16* v_base, const int* page_indices,
+                      const int* page_indptr, const int* last_page_len, const int* q_indptr, int seq_len, int batch_size,
+                      int nq, int nkv, int page_size, int64_t stride_page, float sm_scale_log2, int v_desc_mode,
+                      cudaStream_t stream);
+
+// PK_PREFILL_ATTN = tc | legacy: tcgen05/TMEM kernel or the mma.sync kernel for the paged batch-prefill entry.
+static int prefill_attn_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_PREFILL_ATTN");
+    v = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+  }
+  return v;
+}
+static int prefill_tc_vdesc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_FA_VDESC");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 }  // namespace pk
 
 using namespace pk;
@@ -369,6 +396,11 @@ int batch_prefill_paged_cuda_with_cta_tile_q(
                          head_dim, cta_tile_q_override) == 0)
     return -1;  // invalid tile override, as the reference
   if (seq_len <= 0 || batch_size <= 0) return 0;
+  if (prefill_attn_impl() == 1 && q_indptr && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0)
+    return launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+                             (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d, q_indptr,
+                             seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
+                             sm_scale * 1.44269504088896340736f, prefill_tc_vdesc(), stream);
   PrefillArgs a{};
   a.q = (const bf16*)q; a.out = (bf16*)output;
   a.k_base = (const bf16*)kv_data + k_offset_elems;
@@ -411,6 +443,19 @@ int single_prefill_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16* k_cach
   a.sm_scale_log2 = sm_scale * 1.44269504088896340736f;
   a.contiguous = 1; a.kv_len_single = kv_len; a.max_seq_len = max_seq_len;
   return launch_prefill(a, stream);
+}
+
+int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
+                                 int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
+                                 const int* last_page_len_d, const int* q_indptr, int num_qo_heads, int num_kv_heads,
+                                 int head_dim, int page_size, int seq_len, int batch_size, int64_t stride_page,
+                                 float sm_scale, int v_desc_mode, pk_stream stream) {
+  if (head_dim != PHD || !q_indptr || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0 || page_size <= 0) return -1;
+  if (seq_len <= 0 || batch_size <= 0) return 0;
+  return launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+                           (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d, q_indptr,
+                           seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
+                           sm_scale * 1.44269504088896340736f, v_desc_mode, stream);
 }
 
 }  // extern "C"

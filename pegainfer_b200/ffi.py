@@ -22,6 +22,11 @@ class GemvArgs(C.Structure):
                 ("hidden_out", vp), ("normed_out", vp), ("epi", i32), ("tp_comm", vp)]
 
 
+class PrefetchSpan(C.Structure):
+    """pk_b200_prefetch_span (include/pegainfer_kernels.h)."""
+    _fields_ = [("base", vp), ("rows", i32), ("row_bytes", i32), ("slices", i32), ("prefetch_rows", i32)]
+
+
 # name -> (restype, argtypes); order follows include/pegainfer_kernels.h
 SIGNATURES = {
     "cuda_set_device": (i32, [i32]),
@@ -66,6 +71,10 @@ EXT_SIGNATURES = {
     "pk_b200_set_gemv_tuning": (None, [i32, i32, i32]),
     "pk_b200_decode_step_persistent": (i32, [vp, vp]),
     "pk_b200_decode_attention_fused": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7 + [i64, f32, vp]),
+    "pk_b200_decode_attention_fused_prefetch": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7
+                                                + [i64, f32, C.POINTER(PrefetchSpan), i32, vp]),
+    "pk_b200_gemv_grid": (i32, [i32, i32]),
+    "pk_b200_prefill_attention_tc": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, i32, vp]),
     "pk_tp_flag_bytes": (i64, []),
     "pk_tp_comm_create": (vp, [i32, i32, C.POINTER(vp), C.POINTER(vp), i64]),
     "pk_tp_comm_destroy": (None, [vp]),

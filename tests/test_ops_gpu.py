@@ -514,3 +514,72 @@ def test_gemv_fused_prologue_epilogue(N):
     assert lib.pk_b200_gemv_fused(C.byref(g2), stream()) == 0
     want = O.silu_mul_fused(O.gemm(bits(Wgu), bits(x)), inter)
     assert_bf16_close(bits(act), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what="swiglu gemv")
+
+
+# ------------------------------------------------------------------ fused decode attention (+ L2 prefetch clusters)
+@pytest.mark.parametrize("seq_lens", [[1], [300], [2300, 77]])
+def test_decode_attention_fused_matches_unfused_ops(seq_lens):
+    """pk_b200_decode_attention_fused == qk_norm_rope_batched_decode + paged_kv_scatter + paged_attention_decode
+    (oracle composition, batch_decode.rs:196-247), and the prefetch variant returns the same bits."""
+    lib = get_lib("b200")
+    nq, nkv, hd, layer, bs = 32, 8, 128, 1, len(seq_lens)
+    pg = Paged(seq_lens, nkv, seed=9)
+    L = pg.layout
+    q, k, v = rnd((bs, nq * hd), 40, 2.0), rnd((bs, nkv * hd), 41, 2.0), rnd((bs, nkv * hd), 42)
+    qw, kw = rnd((hd,), 43, 0.3) + 1, rnd((hd,), 44, 0.3) + 1
+    cos, sin = O.precompute_rope(hd, 4096, 1e6)
+    pos = np.array([s - 1 for s in seq_lens], np.int32)
+    sm = 1 / math.sqrt(hd)
+    # oracle: norm+rope -> append -> attention over the full context
+    qn, kn = bits(q).copy(), bits(k).copy()
+    O.qk_norm_rope(qn, kn, bits(qw), bits(kw), cos, sin, nq, nkv, hd, 1e-6, positions=pos)
+    kv_want = bits(pg.kv).copy()
+    O.paged_kv_scatter(kv_want, L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl, kn, bits(v),
+                       np.arange(bs, dtype=np.int32), pos, nkv, hd, 16, L.page_stride)
+    req, tile0, chunk = np.arange(bs, dtype=np.int32), np.zeros(bs, np.int32), np.array(seq_lens, np.int32)
+    want = O.paged_attention_decode(qn, kv_want, L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl, req, tile0,
+                                    chunk, nq, nkv, hd, 16, L.page_stride, sm)
+    max_chunks = 37
+    cos_d, sin_d = from_bits(cos, "cuda"), from_bits(sin, "cuda")
+    _keep.extend([cos_d, sin_d])
+    weights = rnd((4096, 2560), 45)  # stands in for the next GEMVs' weights
+    w_d = dev(weights)
+    spans = (ffi.PrefetchSpan * 2)(ffi.PrefetchSpan(p(w_d), 4096, 5120, lib.pk_b200_gemv_grid(4096, 0), 64),
+                                   ffi.PrefetchSpan(p(w_d), 2048, 5120, lib.pk_b200_gemv_grid(2048, 1), 3))
+    outs = []
+    for use_pf in (False, True):
+        kv_d = dev(pg.kv)
+        out = torch.zeros((bs, nq * hd), dtype=torch.bfloat16, device="cuda")
+        partial = torch.zeros(bs * max_chunks * nq * 130, dtype=torch.float32, device="cuda")
+        counters = torch.zeros(bs * nkv + 16, dtype=torch.int32, device="cuda")
+        common = [p(dev(q)), p(dev(k)), p(dev(v)), p(out), p(kv_d), L.k_offset(layer), L.v_offset(layer), p(i32(pg.pi)),
+                  p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(pos)), p(dev(qw)), p(dev(kw)), p(cos_d), p(sin_d), 1e-6, p(partial), p(counters), 64, max_chunks, nq, nkv, hd, 16, bs,
+                  L.page_stride, sm]
+        _keep.extend([partial, counters])
+        if use_pf:
+            rc = lib.pk_b200_decode_attention_fused_prefetch(*common, spans, 2, stream())
+        else:
+            rc = lib.pk_b200_decode_attention_fused(*common, stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="fused decode attn")
+        # the appended K/V rows are the oracle's bits (norm/rope within 2 ulp -> compare through the attention only),
+        # V rows are plain copies
+        got_kv = bits(kv_d)
+        vmask = got_kv != bits(pg.kv)
+        assert vmask.sum() <= bs * 2 * nkv * hd
+        outs.append(bits(out).copy())
+    assert (outs[0] == outs[1]).all(), "prefetch clusters must not change the result"
+
+
+def test_decode_attention_prefetch_rejects_bad_spans():
+    lib = get_lib("b200")
+    assert lib.pk_b200_gemv_grid(2560, 0) == min(2 * torch.cuda.get_device_properties(0).multi_processor_count, 320)
+    assert lib.pk_b200_gemv_grid(16, 1) == 4
+    bad = (ffi.PrefetchSpan * 1)(ffi.PrefetchSpan(16, 8, 24, 4, 1))  # row_bytes % 16 != 0
+    z = torch.zeros(4096, dtype=torch.bfloat16, device="cuda")
+    zi = torch.zeros(64, dtype=torch.int32, device="cuda")
+    rc = lib.pk_b200_decode_attention_fused_prefetch(p(z), p(z), p(z), p(z), p(z), 0, 0, p(zi), p(zi), p(zi), p(zi), p(z), p(z),
+                                                     p(z), p(z), 1e-6, None, p(zi), 64, 1, 32, 8, 128, 16, 1, 32768, 0.1, bad, 1,
+                                                     stream())
+    assert rc == -1
