@@ -77,8 +77,8 @@ void silu_mul_fused_cuda(const pk_bf16* gate_up, pk_bf16* out, int intermediate_
 /* ---- GEMM / GEMV: ffi.rs:122-140; csrc/linear.cu:48-78 ----------------------
  * Y[M,N] (col-major, ld=M) = W[M,K] (row-major) * X[K,N] (col-major, ld=K);
  * bf16 in, fp32 accumulate, one bf16 rounding.
- * gemm_cuda: prefill (tcgen05 tensor cores).  gemm_graphsafe_cuda: decode; N<=4 runs
- * the HBM-streaming GEMV, larger N the same tensor-core path.  Both are capture safe. */
+ * Both names dispatch alike and are capture safe: N <= 4 runs the HBM-streaming GEMV,
+ * larger N the tcgen05 tensor-core GEMM. */
 void gemm_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
                pk_stream stream);
 void gemm_graphsafe_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
@@ -267,13 +267,14 @@ int pk_b200_decode_attention_fused(
 
 /* Causal GQA prefill attention over the paged cache on tcgen05/TMEM (prefill_attention_tc.cu): the kernel behind
  * batch_prefill_paged_cuda* when PK_PREFILL_ATTN=tc, callable directly.  Same inputs as the ABI entry minus the
- * FlashInfer tile plan (tiles are derived from q_indptr on the device).  v_desc_mode: 0 (bring-up switch for the
- * MN-major V descriptor, see the source).  Returns 0 / cudaError / -1 for unsupported shapes (head_dim != 128). */
+ * FlashInfer tile plan (tiles are derived from q_indptr on the device).  K/V pages are fetched with 4-D TMA tile
+ * loads, so the pool base + offsets must be 16-byte aligned.  Returns 0 / cudaError / -1 for unsupported shapes
+ * (head_dim != 128, page_size != 16). */
 int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
                                  int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
                                  const int* last_page_len_d, const int* q_indptr, int num_qo_heads, int num_kv_heads,
                                  int head_dim, int page_size, int seq_len, int batch_size, int64_t stride_page,
-                                 float sm_scale, int v_desc_mode, pk_stream stream);
+                                 float sm_scale, pk_stream stream);
 
 /* pk_b200_decode_attention_fused plus an L2 prefetch of weights that FOLLOWING launches will stream.
  * bs-1 decode attention is latency-bound (a few MB of K/V against ~10 us of dependent steps) and leaves HBM

@@ -224,26 +224,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 }
 
 // ---- host side ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // rows x K bf16 row-major matrix, box = [box_rows, 64], 128-byte swizzle, OOB reads as zero
 static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
   EncodeTiledFn fn = encode_fn();
@@ -351,7 +331,9 @@ extern "C" int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16
   return 0;
 }
 
+// Same dispatch as gemm_graphsafe_cuda (gemv.cu): N <= 4 streams the weights (HBM-bound GEMV), larger N runs on the
+// tensor cores.  Neither path allocates or synchronises, so both ABI names are capture-safe here.
 extern "C" void gemm_cuda(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K,
                           pk_stream stream) {
-  pk::launch_gemm((const pk::bf16*)W, (const pk::bf16*)X, (pk::bf16*)Y, M, N, K, stream);
+  gemm_graphsafe_cuda(W, X, Y, M, N, K, stream);
 }

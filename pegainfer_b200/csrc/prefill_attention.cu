@@ -7,11 +7,12 @@
 // product and the denominator is the row sum of the ROUNDED P (prefill.cuh:956-985); O
 // accumulates in fp32 and O/d is rounded once to bf16.
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 bf16 tensor-core tiles (one warp = 16 query
+// This file: warp-level mma.sync.m16n8k16 bf16 tensor-core tiles (one warp = 16 query
 // tokens of one q head; a CTA covers 8/GROUP token blocks x GROUP heads of one kv head so every
 // K/V tile staged in shared memory is reused by the whole GQA group), cp.async double-buffered
 // 64-token K/V tiles gathered from 16-token pages, XOR-swizzled rows (conflict-free ldmatrix).
-// The tcgen05/TMEM version of this kernel is the next step (DESIGN.md "what comes next").
+// The paged batch-prefill entry runs the tcgen05/TMEM kernel of prefill_attention_tc.cu by default; this kernel
+// serves single_prefill_cuda (contiguous K/V), page sizes other than 16 and PK_PREFILL_ATTN=legacy (A/B).
 //
 // The caller's tile plan (request_indices / qo_tile_indices / kv_tile_indices) is ignored
 // consistently: tiles are derived from q_indptr on the device; results do not depend on tiling.
@@ -333,27 +334,17 @@ static int resolve_cta_tile_q(int64_t packed_qo_len, int head_dim, int override_
 // prefill_attention_tc.cu
 int launch_prefill_tc(const bf16* q, bf16* out, const bf16* k_base, const bf16* v_base, const int* page_indices,
                       const int* page_indptr, const int* last_page_len, const int* q_indptr, int seq_len, int batch_size,
-                      int nq, int nkv, int page_size, int64_t stride_page, float sm_scale_log2, int v_desc_mode,
-                      cudaStream_t stream);
+                      int nq, int nkv, int page_size, int64_t stride_page, float sm_scale_log2, cudaStream_t stream);
 
-// PK_PREFILL_ATTN = tc | legacy: tcgen05/TMEM kernel or the mma.sync kernel for the paged batch-prefill entry.
+// PK_PREFILL_ATTN = tc (default) | legacy: tcgen05/TMEM kernel or the mma.sync kernel for the paged batch-prefill entry.
 static int prefill_attn_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PK_PREFILL_ATTN");
-    v = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
   }
   return v;
 }
-static int prefill_tc_vdesc() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PK_FA_VDESC");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 }  // namespace pk
 
 using namespace pk;
@@ -396,11 +387,13 @@ int batch_prefill_paged_cuda_with_cta_tile_q(
                          head_dim, cta_tile_q_override) == 0)
     return -1;  // invalid tile override, as the reference
   if (seq_len <= 0 || batch_size <= 0) return 0;
-  if (prefill_attn_impl() == 1 && q_indptr && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0)
-    return launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
-                             (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d, q_indptr,
-                             seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
-                             sm_scale * 1.44269504088896340736f, prefill_tc_vdesc(), stream);
+  if (prefill_attn_impl() == 1 && q_indptr && page_size == 16 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0) {
+    const int rc = launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+                                     (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d,
+                                     q_indptr, seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
+                                     sm_scale * 1.44269504088896340736f, stream);
+    if (rc != -2) return rc;  // -2: pool not expressible as a TMA tensor map -> mma.sync kernel below
+  }
   PrefillArgs a{};
   a.q = (const bf16*)q; a.out = (bf16*)output;
   a.k_base = (const bf16*)kv_data + k_offset_elems;
@@ -449,13 +442,14 @@ int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf1
                                  int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
                                  const int* last_page_len_d, const int* q_indptr, int num_qo_heads, int num_kv_heads,
                                  int head_dim, int page_size, int seq_len, int batch_size, int64_t stride_page,
-                                 float sm_scale, int v_desc_mode, pk_stream stream) {
-  if (head_dim != PHD || !q_indptr || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0 || page_size <= 0) return -1;
+                                 float sm_scale, pk_stream stream) {
+  if (head_dim != PHD || !q_indptr || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0 || page_size != 16) return -1;
   if (seq_len <= 0 || batch_size <= 0) return 0;
-  return launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
-                           (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d, q_indptr,
-                           seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
-                           sm_scale * 1.44269504088896340736f, v_desc_mode, stream);
+  const int rc = launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+                                   (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d,
+                                   q_indptr, seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
+                                   sm_scale * 1.44269504088896340736f, stream);
+  return rc == -2 ? -1 : rc;
 }
 
 }  // extern "C"

@@ -3,6 +3,8 @@
 // SBO>>4 [32,46), version=1 [46,48), layout [61,64); instruction descriptor: D fmt [4,6), A fmt [7,10), B fmt [10,13),
 // A major [15], B major [16], N>>3 [17,23), M>>4 [24,29)).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace pk {
@@ -80,6 +82,27 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint3
 // generic-proxy shared-memory writes (st.shared, cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
 
 }  // namespace pk

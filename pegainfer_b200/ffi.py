@@ -74,7 +74,7 @@ EXT_SIGNATURES = {
     "pk_b200_decode_attention_fused_prefetch": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7
                                                 + [i64, f32, C.POINTER(PrefetchSpan), i32, vp]),
     "pk_b200_gemv_grid": (i32, [i32, i32]),
-    "pk_b200_prefill_attention_tc": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, i32, vp]),
+    "pk_b200_prefill_attention_tc": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, vp]),
     "pk_tp_flag_bytes": (i64, []),
     "pk_tp_comm_create": (vp, [i32, i32, C.POINTER(vp), C.POINTER(vp), i64]),
     "pk_tp_comm_destroy": (None, [vp]),

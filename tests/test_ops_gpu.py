@@ -583,3 +583,31 @@ def test_decode_attention_prefetch_rejects_bad_spans():
                                                      p(z), p(z), 1e-6, None, p(zi), 64, 1, 32, 8, 128, 16, 1, 32768, 0.1, bad, 1,
                                                      stream())
     assert rc == -1
+
+
+# ------------------------------------------------------------------ tcgen05 prefill attention (direct entry)
+@pytest.mark.parametrize("starts,lens,nq,nkv", [([0], [128], 32, 8), ([0, 0, 0], [33, 100, 5], 32, 8), ([40], [60], 32, 8),
+                                                ([0], [300], 4, 1), ([100, 0], [700, 129], 32, 8)])
+def test_prefill_attention_tc(starts, lens, nq, nkv):
+    """The tcgen05/TMEM flash-attention kernel (TMA page loads, MN-major V operand) against the oracle, same
+    tolerance as the mma.sync kernel behind the ABI entry (test_batch_prefill_paged)."""
+    lib = get_lib("b200")
+    hd, layer, bs = 128, 1, len(lens)
+    kv_lens = [s + n for s, n in zip(starts, lens)]
+    pg = Paged(kv_lens, nkv, seed=6)
+    L = pg.layout
+    T = sum(lens)
+    q = rnd((T, nq * hd), 35)
+    out = torch.zeros((T, nq * hd), dtype=torch.bfloat16, device="cuda")
+    q_indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    sm = 1 / math.sqrt(hd)
+    rc = lib.pk_b200_prefill_attention_tc(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
+                                          p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(q_indptr)), nq, nkv, hd, 16, T,
+                                          bs, L.page_stride, sm, stream())
+    assert rc == 0
+    want = O.batch_prefill_paged(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl,
+                                 q_indptr, nq, nkv, hd, 16, L.page_stride, sm)
+    assert_bf16_close(bits(out), want, 8, floor=float(np.abs(f32(want)).max()) / 32, what="tc prefill attn")
+    assert lib.pk_b200_prefill_attention_tc(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
+                                            p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(q_indptr)), nq, nkv, hd, 32,
+                                            T, bs, L.page_stride, sm, stream()) == -1  # page size 32: unsupported

@@ -1,6 +1,6 @@
 """Bring-up / regression check of the tcgen05 prefill attention kernel against the CPU oracle, one process per run.
 
-    python tools/check_prefill_tc.py [v_desc_mode] [case ...]     cases: small ragged long batch (default: all)
+    python tools/check_prefill_tc.py [case ...]     cases: small ragged offset mid long batch (default: all)
 
 Prints per case the max error in bf16 ulps (floor = max|want| / 32) and a timing for the long case.
 """
@@ -28,8 +28,7 @@ CASES = {
 
 
 def main():
-    mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-    names = sys.argv[2:] or list(CASES)
+    names = sys.argv[1:] or list(CASES)
     lib = ffi.lib()
     torch.zeros(1, device="cuda")
     lib.cuda_set_device(0)
@@ -60,7 +59,7 @@ def main():
         sm = 1 / math.sqrt(hd)
         call = lambda: lib.pk_b200_prefill_attention_tc(q_d.data_ptr(), out.data_ptr(), kv_d.data_ptr(), L.k_offset(layer), L.v_offset(layer),
                                                         pi_d.data_ptr(), ip_d.data_ptr(), lpl_d.data_ptr(), qi_d.data_ptr(), nq, nkv, hd, 16, T, bs,
-                                                        L.page_stride, sm, mode, st)
+                                                        L.page_stride, sm, st)
         rc = call()
         torch.cuda.synchronize()
         want = O.batch_prefill_paged(bits(q), bits(kv), L.k_offset(layer), L.v_offset(layer), np.array(pi, np.int32), np.array(ip, np.int32),
@@ -68,7 +67,7 @@ def main():
         e = ulp_err(bits(out).ravel(), np.asarray(want).ravel(), float(np.abs(f32(want)).max()) / 32)
         ok = rc == 0 and np.isfinite(e).all() and e.max() <= 8
         ok_all &= bool(ok)
-        msg = f"TC_ATTN mode={mode} case={name} rc={rc} max_ulp={e.max():.2f} mean_ulp={e.mean():.3f} {'OK' if ok else 'FAIL'}"
+        msg = f"TC_ATTN case={name} rc={rc} max_ulp={e.max():.2f} mean_ulp={e.mean():.3f} {'OK' if ok else 'FAIL'}"
         if name in ("long", "batch"):
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             for _ in range(3):
