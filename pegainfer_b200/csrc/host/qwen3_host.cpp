@@ -745,18 +745,18 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
     return true;
   };
   // Tensor parallel, two variants (both custom kernels over NVLink peer memory, no NCCL on the data path):
-  //  * fused (default for world <= 2; PK_TP_FUSED=1): the row-parallel GEMVs (o_proj, down_proj) push their
-  //    partial rows to every rank (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches
-  //    per layer, the layer's two all-reduces live inside the GEMVs.
-  //  * kernel (default for world >= 4; PK_TP_FUSED=0): one-shot all-reduce kernel fused with add + RMSNorm between
-  //    the GEMVs (7 launches per layer).  Measured on 8 x B200 (Qwen3-8B, bs 1): 411 tok/s vs 350 tok/s for the
-  //    fused variant -- with 7 peers the per-CTA system-scope fence + grid ticket of the push epilogue costs more
-  //    than a single-CTA collective; at 2 GPUs the fused variant wins (339 vs 323 tok/s).
+  //  * kernel (default): one-shot all-reduce kernel fused with add + RMSNorm between the GEMVs (7 launches/layer).
+  //  * fused (PK_TP_FUSED=1): the row-parallel GEMVs (o_proj, down_proj) push their partial rows to every rank
+  //    (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches per layer, the layer's two
+  //    all-reduces live inside the GEMVs.
+  //  Measured (Qwen3-8B, bs 1, profiles/README.md): 2 x B200 398 vs 367 tok/s, 8 x B200 411 vs 350 tok/s -- every one
+  //  of the push epilogue's ~300 CTAs pays a system-scope fence after its remote stores and the grid ticket
+  //  serialises behind them, which costs more than a single-CTA collective launch.  Kept as an opt-in experiment.
   static const int tp_fused_env = [] {
     const char* e = getenv("PK_TP_FUSED");
     return e ? atoi(e) : -1;
   }();
-  const bool tp_fuse = tp_on && (tp_fused_env >= 0 ? tp_fused_env != 0 : tp.world_size <= 2);
+  const bool tp_fuse = tp_on && tp_fused_env > 0;
   const int red_mode = tp_on ? 2 : 1;
   const int push_epi = tp_on ? 2 : 0;
   const pk_bf16* prev_residual = zero_residual.bf();  // layer 0: hidden + 0

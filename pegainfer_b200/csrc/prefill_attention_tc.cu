@@ -14,9 +14,10 @@
 //                        is [kv token][head dim], i.e. N-contiguous) into a third TMEM region; only the k-steps whose
 //                        16-token page was loaded are issued
 //   softmax warps (0-7): two threads per query row (warps w and w+4 share TMEM lane quadrant w): each owns 64 of the
-//                        128 score columns and 64 of the 128 output columns; row maxima are exchanged through shared
-//                        memory (one named barrier per block), the denominators only once at the end.  One
-//                        tcgen05.ld pass over S (64 values in registers), bf16 P -> swizzled smem; the previous
+//                        128 score columns and 64 of the 128 output columns.  Each reads the whole S row from TMEM
+//                        for the row maximum (the partner's half is reduced and dropped), so the loop has no
+//                        cross-warp exchange; the denominators are combined once at the end.  bf16 P -> swizzled
+//                        smem; the previous
 //                        block's O = O * alpha + (P V) fold (O in 64 registers per thread) is deferred until just
 //                        before P is rewritten, so P V runs under the next block's exponentials.  Blocks fully
 //                        below the diagonal skip the per-element mask.
@@ -80,12 +81,6 @@ __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" 
 __device__ __forceinline__ uint32_t sw_off(int r, int c16) {
   return (uint32_t)((c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
 }
-// 64 consecutive TMEM columns of this thread's lane
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* v) {
-  tmem_ld32(taddr, v);
-  tmem_ld32(taddr + 32, v + 32);
-}
-
 __global__ void __launch_bounds__(T_THREADS, 1)
 prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                             const PrefillTcArgs a) {
@@ -251,6 +246,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
     const bool row_ok = tok < qo_len;
     const int lim = row_ok ? min(kv_len - 1, tok + causal_off) : -1;  // last kv index this row may see
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * 64);
+    const uint32_t t_lane_other = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((hh ^ 1) * 64);
     float o[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
@@ -273,31 +269,40 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
       const int sb = j & 1;
       mbar_wait_or_trap(s_full + sb, (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      uint32_t v[64];
-      tmem_ld64(t_lane + (uint32_t)(sb * TKV), v);
-      const int col0 = j * TKV + hh * 64;  // kv index of v[0]
+      // Row maximum over all 128 columns, in raw score units (the scale is positive, so max and scale commute
+      // exactly): the partner thread's 64 columns are reduced and dropped, ours are kept.  Both threads of a row
+      // compute the same maximum from the same data -- no exchange, no barrier inside the loop.
       const bool masked = !__all_sync(0xffffffffu, j * TKV + TKV - 1 <= lim);  // warp-uniform
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t w[32];
+        tmem_ld32(t_lane_other + (uint32_t)(sb * TKV + h2 * 32), w);
+        if (masked) {
+          const int c_other = j * TKV + (hh ^ 1) * 64 + h2 * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], c_other + i <= lim ? __uint_as_float(w[i]) : -INFINITY);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(w[i]));
+        }
+      }
+      uint32_t v[64];
+      tmem_ld32(t_lane + (uint32_t)(sb * TKV), v);
+      tmem_ld32(t_lane + (uint32_t)(sb * TKV + 32), v + 32);
       if (masked) {
+        const int col0 = j * TKV + hh * 64;  // kv index of v[0]
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-          const float s = col0 + i <= lim ? __uint_as_float(v[i]) * a.sm_scale_log2 : -INFINITY;
-          v[i] = __float_as_uint(s);
-          mx4[i & 3] = fmaxf(mx4[i & 3], s);
+          if (col0 + i > lim) v[i] = 0xff800000u;  // -inf -> P = 0
+          mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float s = __uint_as_float(v[i]) * a.sm_scale_log2;
-          v[i] = __float_as_uint(s);
-          mx4[i & 3] = fmaxf(mx4[i & 3], s);
-        }
+        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      float* xb = xch + (j & 1) * 256;
-      xb[hh * 128 + r] = mx;
-      softmax_bar();
-      const float m_new = fmaxf(m, fmaxf(mx, xb[(hh ^ 1) * 128 + r]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.sm_scale_log2;
+      const float m_new = fmaxf(m, mx);
       const float ref = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = tex2(m - ref);  // m = -inf -> 0
       m = m_new;
@@ -307,7 +312,8 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
       float ds4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const uint32_t pk = pack_bf16(tex2(__uint_as_float(v[2 * i]) - ref), tex2(__uint_as_float(v[2 * i + 1]) - ref));
+        const uint32_t pk = pack_bf16(tex2(fmaf(__uint_as_float(v[2 * i]), a.sm_scale_log2, -ref)),
+                                      tex2(fmaf(__uint_as_float(v[2 * i + 1]), a.sm_scale_log2, -ref)));
         ds4[i & 3] += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
         v[i] = pk;
       }
@@ -324,7 +330,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
     }
     if (n_blocks > 0) fold_pv(n_blocks - 1, alpha_prev);
     // denominators of the two column halves
-    float* xb = xch + (n_blocks & 1) * 256;
+    float* xb = xch;
     xb[hh * 128 + r] = d;
     softmax_bar();
     d += xb[(hh ^ 1) * 128 + r];

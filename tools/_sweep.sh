@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-timeout 150 python tools/check_prefill_tc.py > gpurun_out/tc0.log 2>&1; echo "tc rc=$?"; tail -8 gpurun_out/tc0.log
-if grep -q "TC_ATTN_ALL PASS" gpurun_out/tc0.log; then
-timeout 300 python -m pytest tests/test_model_gpu.py tests/test_ops_gpu.py -m gpu -x -q -k "prefill or parity or generate" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-timeout 200 ncu --set full --import-source on --clock-control none -k regex:prefill_attention_tc -s 1 -c 1 -o gpurun_out/fa_tc_long python tools/check_prefill_tc.py long > gpurun_out/ncu_tc.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_tc.log
-fi
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 200 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; cat gpurun_out/bench_final.json | cut -c1-400
+timeout 200 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; cat gpurun_out/bench_reference.json | cut -c1-300
+timeout 250 ncu --metrics gpu__time_duration.sum --clock-control none -c 1100 --csv --log-file gpurun_out/r1_v6_prefill_decode_launches.csv python tools/profile_decode.py 2048 3 0 > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
+timeout 200 python tools/bench_decode_micro.py > gpurun_out/micro.json 2> gpurun_out/micro.err; echo "micro rc=$?"
+timeout 100 python tools/bench_prefill_ops.py > gpurun_out/prefill_ops.log 2>&1; tail -8 gpurun_out/prefill_ops.log
