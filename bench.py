@@ -112,7 +112,7 @@ def cpu_decode_rate(cfg, weights_np, steps, budget_s, ctx=16):
     """Time `steps` full-depth greedy decode steps of the CPU oracle (OpenMP, all host cores).
     Context is `ctx` tokens (the weight stream is > 96 % of the bytes at the metric's ctx anyway)."""
     from pegainfer_b200.synthetic import synthetic_prompt
-    O, orc = make_oracle(cfg, weights_np, num_pages=8)
+    O, orc = make_oracle(cfg, weights_np, num_pages=(ctx + steps + 2) // 16 + 4)  # whole run fits: prompt + warm-up + steps
     kv = orc.alloc_kv()
     lg = orc.prefill([synthetic_prompt(ctx)], [kv])[0]
     tok = O.argmax(lg)

@@ -511,6 +511,18 @@ int paged_attention_decode_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16
   (void)kv_chunk_size_ptr;
   if (head_dim != HD || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0) return -1;
   if (batch_size <= 0) return 0;
+  if (num_qo_heads == 4 * num_kv_heads && page_size == 16 && use_cluster_attention()) {
+    // 8-CTA cluster per (request, kv head) with the merge over distributed shared memory: fp32 throughout, as the
+    // reference's non-partition kernel
+    ClusterAttnArgs c{};
+    c.q = (const bf16*)q; c.out = (bf16*)output; c.kv = (bf16*)kv_data;
+    c.k_off = k_offset_elems; c.v_off = v_offset_elems; c.stride_page = stride_page;
+    c.page_indices = page_indices; c.page_indptr = page_indptr; c.last_page_len = last_page_len_d;
+    c.request_indices = request_indices;
+    c.sm_scale_log2 = sm_scale * 1.44269504088896340736f;
+    c.nq = num_qo_heads; c.nkv = num_kv_heads;
+    return (int)launch_decode_attention_cluster(c, num_kv_heads, batch_size, stream);
+  }
   ThreadState& ts = tls();
   // scratch layout: [counters: bs*nkv ints, padded to 4 KB][fp32 partials]
   const size_t counter_bytes = 4096 + (((size_t)batch_size * num_kv_heads * 4 + 4095) & ~(size_t)4095);

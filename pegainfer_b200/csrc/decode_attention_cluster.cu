@@ -121,14 +121,18 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int rank = (int)cluster_rank();
-  const int kvh = blockIdx.y, b = blockIdx.z;
+  // plain mode (the ABI's paged_attention_decode_cuda): q arrives normed + roped, the step's K/V row was appended
+  // by an earlier launch -> no norm, no injection, and no K/V request before griddepcontrol.wait
+  const bool plain = a.k_new == nullptr;
+  const int kvh = blockIdx.y;
+  const int b = (plain && a.request_indices) ? a.request_indices[blockIdx.z] : (int)blockIdx.z;
   const int npages = a.page_indptr[b + 1] - a.page_indptr[b];
   const int len = npages <= 0 ? 0 : (npages - 1) * 16 + a.last_page_len[b];
   int chunk = (len + C_CLUSTER - 1) / C_CLUSTER;
   chunk = (chunk + C_ROUND - 1) / C_ROUND * C_ROUND;
   const int lo = min(len, rank * chunk), hi = min(len, lo + chunk);
   const int* pages = a.page_indices + a.page_indptr[b];
-  const int pos = a.positions[b];
+  const int pos = plain ? -1 : a.positions[b];
   const bool inject = pos >= lo && pos < hi;
   const bf16* kbase = a.kv + a.k_off + (int64_t)kvh * CHD + l16 * 8;
   const bf16* vbase = a.kv + a.v_off + (int64_t)kvh * CHD + l16 * 8;
@@ -155,14 +159,17 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
       }
     }
   };
-  load_round(lo, kr, vr, ok);
+  if (!plain) load_round(lo, kr, vr, ok);
 
   pdl_wait();
+  if (plain) load_round(lo, kr, vr, ok);
 
   // ---- q heads (warps 0-3), the step's k/v (warp 4 of the owning CTA) ----
-  if (warp < C_GROUP)
-    c_norm_rope(a.q + ((size_t)b * a.nq + kvh * C_GROUP + warp) * CHD, a.qw, a.cosc, a.sinc, pos, a.eps, q_s[warp],
-                lane);
+  if (warp < C_GROUP) {
+    const bf16* qsrc = a.q + ((size_t)b * a.nq + kvh * C_GROUP + warp) * CHD;
+    if (plain) reinterpret_cast<uint2*>(q_s[warp])[lane] = reinterpret_cast<const uint2*>(qsrc)[lane];
+    else c_norm_rope(qsrc, a.qw, a.cosc, a.sinc, pos, a.eps, q_s[warp], lane);
+  }
   if (inject && warp == C_GROUP) {
     c_norm_rope(a.k_new + ((size_t)b * a.nkv + kvh) * CHD, a.kw, a.cosc, a.sinc, pos, a.eps, k_s, lane);
     reinterpret_cast<uint2*>(v_s)[lane] = reinterpret_cast<const uint2*>(a.v_new + ((size_t)b * a.nkv + kvh) * CHD)[lane];

@@ -20,6 +20,7 @@ struct ClusterAttnArgs {
   bf16* kv;
   int64_t k_off, v_off, stride_page;
   const int *page_indices, *page_indptr, *last_page_len, *positions;
+  const int* request_indices;  // plain mode (k_new == nullptr): batch slot -> request, may be null (identity)
   const bf16 *qw, *kw, *cosc, *sinc;
   float eps, sm_scale_log2;
   int nq, nkv;
