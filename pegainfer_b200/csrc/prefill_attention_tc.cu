@@ -256,12 +256,13 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
     auto fold_pv = [&](int jj, float alpha) {
       mbar_wait_or_trap(pv_full, (uint32_t)(jj & 1));
       tc_fence_after();
+      {
+        uint32_t t[64];
+        tmem_ld32_nowait(t_pv, t);
+        tmem_ld32_nowait(t_pv + 32, t + 32);
+        tmem_ld_wait64(t);
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t t[32];
-        tmem_ld32(t_pv + (uint32_t)(h2 * 32), t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[h2 * 32 + i] = fmaf(o[h2 * 32 + i], alpha, __uint_as_float(t[i]));
+        for (int i = 0; i < 64; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(t[i]));
       }
       tc_fence_before();  // the PV region is rewritten only after our next p_full arrival
     };
@@ -274,22 +275,24 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
       // compute the same maximum from the same data -- no exchange, no barrier inside the loop.
       const bool masked = !__all_sync(0xffffffffu, j * TKV + TKV - 1 <= lim);  // warp-uniform
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t w[32];
-        tmem_ld32(t_lane_other + (uint32_t)(sb * TKV + h2 * 32), w);
+      {
+        uint32_t w[64];
+        tmem_ld32_nowait(t_lane_other + (uint32_t)(sb * TKV), w);
+        tmem_ld32_nowait(t_lane_other + (uint32_t)(sb * TKV + 32), w + 32);
+        tmem_ld_wait64(w);
         if (masked) {
-          const int c_other = j * TKV + (hh ^ 1) * 64 + h2 * 32;
+          const int c_other = j * TKV + (hh ^ 1) * 64;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], c_other + i <= lim ? __uint_as_float(w[i]) : -INFINITY);
+          for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], c_other + i <= lim ? __uint_as_float(w[i]) : -INFINITY);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(w[i]));
+          for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(w[i]));
         }
       }
       uint32_t v[64];
-      tmem_ld32(t_lane + (uint32_t)(sb * TKV), v);
-      tmem_ld32(t_lane + (uint32_t)(sb * TKV + 32), v + 32);
+      tmem_ld32_nowait(t_lane + (uint32_t)(sb * TKV), v);
+      tmem_ld32_nowait(t_lane + (uint32_t)(sb * TKV + 32), v + 32);
+      tmem_ld_wait64(v);
       if (masked) {
         const int col0 = j * TKV + hh * 64;  // kv index of v[0]
 #pragma unroll
