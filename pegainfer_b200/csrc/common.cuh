@@ -163,6 +163,7 @@ struct TpDev {
   uint32_t* flags[kTpMaxWorld];  // flags[p]: rank p's flag array  [2][kTpMaxCtas][world] + ctl
   int rank, world;
   int64_t slot_bytes;            // bytes per (slot, src) region
+  int64_t raw_bytes;             // leading part of a region used for plain rows; the tail is the LL area
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {

@@ -517,7 +517,7 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
   if (g->x_mode == 2 || g->epi == 2) {
     const pk_tp_comm* comm = static_cast<const pk_tp_comm*>(g->tp_comm);
     if (!comm) return -1;
-    if ((int64_t)g->N * (g->epi == 2 ? g->M : g->K) * 2 > comm->d.slot_bytes) return -2;
+    if ((int64_t)g->N * (g->epi == 2 ? g->M : g->K) * 2 > comm->d.raw_bytes) return -2;
     a.tp = comm->d;
   }
   return (int)launch_gemv(a, g->N, stream);

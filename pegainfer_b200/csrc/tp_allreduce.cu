@@ -12,6 +12,13 @@
 // slots alternate by sequence parity: a peer can be at most one collective ahead.  The sequence
 // counter lives in device memory and is advanced by the kernel, so the launch is CUDA-graph
 // replayable.  One process per GPU: peers map each other's staging with cudaIpc handles.
+//
+// Second protocol (PK_TP_PROTO=ll, opt-in until measured on hardware): the flag travels WITH the data.  Every
+// 16-byte line carries {2 bf16, seq, 2 bf16, seq}; a line is stored and loaded with one volatile 16-byte access,
+// so the receiver simply polls each line until both sequence words match -- no system-scope fence, no separate
+// flag store, no block barrier between push and reduce.  Same rank-ordered fp32 sum, bit-identical results.
+// The lines live in the tail (`slot_bytes - raw_bytes`) of every staging region, never shared with plain rows.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,6 +35,16 @@ struct TpArgs {
   float eps;
 };
 
+__device__ __forceinline__ void st_volatile_v4(void* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool LL>
 __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a) {
   extern __shared__ float tp_row[];  // mode 1: dim floats + 40
   const int me = a.d.rank, W = a.d.world;
@@ -46,22 +63,29 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
       const uint4 v = src[i];
       for (int p = 0; p < W; ++p) {
         if (p == me) continue;
-        uint4* dst = reinterpret_cast<uint4*>(a.d.stage[p] + (size_t)(slot * W + me) * a.d.slot_bytes +
-                                              (size_t)t * a.dim * 2);
-        dst[i] = v;
+        uint8_t* region = a.d.stage[p] + (size_t)(slot * W + me) * a.d.slot_bytes;
+        if (LL) {
+          uint8_t* line = region + a.d.raw_bytes + ((size_t)t * nv + i) * 32;
+          st_volatile_v4(line, v.x, seq, v.y, seq);
+          st_volatile_v4(line + 16, v.z, seq, v.w, seq);
+        } else {
+          reinterpret_cast<uint4*>(region + (size_t)t * a.dim * 2)[i] = v;
+        }
       }
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < W && (int)threadIdx.x != me) {
-    const int p = threadIdx.x;
-    st_release_sys(a.d.flags[p] + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + me, seq);
-    const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + p;
-    while (ld_acquire_sys(f) != seq) {
+  if (!LL) {
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < W && (int)threadIdx.x != me) {
+      const int p = threadIdx.x;
+      st_release_sys(a.d.flags[p] + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + me, seq);
+      const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + p;
+      while (ld_acquire_sys(f) != seq) {
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- reduce in rank order from local memory ----
   const uint8_t* local = a.d.stage[me] + (size_t)slot * W * a.d.slot_bytes;
@@ -72,11 +96,18 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int r = 0; r < W; ++r) {
         uint4 v;
-        if (r == me)
+        if (r == me) {
           v = reinterpret_cast<const uint4*>(a.partial + (size_t)t * a.dim)[i];
-        else
+        } else if (LL) {
+          const uint8_t* line = local + (size_t)r * a.d.slot_bytes + a.d.raw_bytes + ((size_t)t * nv + i) * 32;
+          uint4 l0, l1;
+          do { l0 = ld_volatile_v4(line); } while (l0.y != seq || l0.w != seq);
+          do { l1 = ld_volatile_v4(line + 16); } while (l1.y != seq || l1.w != seq);
+          v = make_uint4(l0.x, l0.z, l1.x, l1.z);
+        } else {
           v = __ldcg(reinterpret_cast<const uint4*>(local + (size_t)r * a.d.slot_bytes +
                                                     (size_t)t * a.dim * 2) + i);
+        }
         acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
         acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
       }
@@ -138,6 +169,15 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
 
 using namespace pk;
 
+static bool tp_use_ll() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_TP_PROTO");
+    v = (e && strcmp(e, "ll") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 extern "C" {
 
 pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
@@ -153,6 +193,8 @@ pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
   }
   c->staging_bytes = staging_bytes;
   c->d.slot_bytes = (staging_bytes / (2 * world)) & ~(int64_t)15;
+  // plain rows use the whole region unless the LL protocol is on, which reserves the last quarter for its lines
+  c->d.raw_bytes = tp_use_ll() ? ((c->d.slot_bytes - c->d.slot_bytes / 4) & ~(int64_t)15) : c->d.slot_bytes;
   return c;
 }
 
@@ -164,7 +206,7 @@ static int tp_launch(pk_tp_comm* comm, const pk_bf16* partial, pk_bf16* hidden,
                      const pk_bf16* weight, pk_bf16* out, int dim, int T, float eps, int mode,
                      pk_stream stream) {
   if (!comm || dim % 8 != 0 || T <= 0) return -1;
-  if ((int64_t)T * dim * 2 > comm->d.slot_bytes) return -2;  // caller chunks larger messages
+  if ((int64_t)T * dim * 2 > comm->d.raw_bytes) return -2;  // caller chunks larger messages
   TpArgs a{};
   a.d = comm->d;
   a.partial = (const bf16*)partial;
@@ -174,7 +216,10 @@ static int tp_launch(pk_tp_comm* comm, const pk_bf16* partial, pk_bf16* hidden,
   a.dim = dim; a.T = T; a.mode = mode; a.eps = eps;
   const int grid = T < kTpMaxCtas ? T : kTpMaxCtas;
   const size_t smem = mode == 1 ? sizeof(float) * ((size_t)dim + 40) : sizeof(float) * 40;
-  return (int)launch(tp_allreduce_kernel, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
+  // LL lines need 4 bytes per element; messages that do not fit the LL area use the flag protocol
+  const bool ll = tp_use_ll() && (int64_t)T * dim * 4 <= comm->d.slot_bytes - comm->d.raw_bytes;
+  if (ll) return (int)launch(tp_allreduce_kernel<true>, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
+  return (int)launch(tp_allreduce_kernel<false>, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
 }
 
 int pk_tp_all_reduce(pk_tp_comm* comm, pk_bf16* hidden, int64_t n, pk_stream stream) {
@@ -202,7 +247,7 @@ int pk_tp_all_reduce_add_rms_norm(pk_tp_comm* comm, pk_bf16* hidden, const pk_bf
 
 int64_t pk_tp_max_rows(pk_tp_comm* comm, int hidden_dim) {
   if (!comm || hidden_dim <= 0) return 0;
-  return comm->d.slot_bytes / ((int64_t)hidden_dim * 2);
+  return comm->d.raw_bytes / ((int64_t)hidden_dim * 2);
 }
 
 // cudaIpc plumbing for the one-process-per-GPU model (handles travel over torch.distributed)

@@ -35,7 +35,8 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     ok = True
     # ---- (1a) in-place all-reduce, several sizes, repeated (sequence / slot reuse) ----
-    for T in (1, 3, 64, 200):
+    t_max = min(200, int(lib.pk_tp_max_rows(comm, H)))  # the LL protocol (PK_TP_PROTO=ll) reserves part of each region
+    for T in (1, 3, 64, t_max):
         for rep in range(3):
             g = torch.Generator(device="cuda").manual_seed(1000 * rep + 10 * T + rank)
             x = torch.randn((T, H), generator=g, device="cuda").to(torch.bfloat16)
