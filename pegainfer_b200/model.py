@@ -126,6 +126,16 @@ class Qwen3Model:
             self._ck(self._h.pq_model_load_tensor(self._m, name.encode(), t.data_ptr(), rows, cols))
         self._ck(self._h.pq_model_finalize(self._m))
 
+    @classmethod
+    def from_safetensors(cls, model_path: str, runtime: ModelRuntimeConfig | None = None, tp_comm: int | None = None):
+        """``Qwen3Model::from_safetensors_with_runtime`` (weights.rs:83-125): ``config.json`` + ``model.safetensors`` (or the
+        sharded index) of an HF Qwen3 checkpoint in bf16.  ``stop_token_ids`` of the checkpoint end up on the instance."""
+        from .weights import iter_safetensors, load_config
+        cfg, stop = load_config(model_path)
+        m = cls(cfg, iter_safetensors(model_path, cfg), runtime, tp_comm)
+        m.stop_token_ids = stop
+        return m
+
     def _ck(self, rc):
         if rc != 0:
             raise RuntimeError(self._h.pq_last_error(self._m).decode())
