@@ -57,3 +57,27 @@ def test_gated_delta_rule_step_matches_hf_recurrence():
         out = gated_delta_rule_step(q[t], k[t], v[t], a[t], b[t], FX["gdr_dt_bias"], FX["gdr_a_log"], S)
         # HF normalises with eps 1e-6 (reference kernel: 1e-12) -> identical to ~1e-6 relative
         np.testing.assert_allclose(out, FX["gdr_out"][t], rtol=2e-4, atol=2e-5)
+
+
+def test_chunkwise_form_equals_the_recurrence():
+    """oracle/qwen35_chunkwise.py (the matrix form the B200 prefill kernel will implement) against the per-token rule."""
+    from oracle.qwen35_chunkwise import gated_delta_rule_chunkwise
+    rng = np.random.RandomState(3)
+    T, nk, nv, dk, dv = 150, 2, 4, 32, 16
+    q, k = rng.randn(T, nk, dk).astype(np.float32), rng.randn(T, nk, dk).astype(np.float32)
+    v, a, b = rng.randn(T, nv, dv).astype(np.float32), rng.randn(T, nv).astype(np.float32), rng.randn(T, nv).astype(np.float32)
+    dt_bias, a_log = (rng.randn(nv) * 0.5).astype(np.float32), (rng.randn(nv) * 0.5).astype(np.float32)
+    S = (rng.randn(nv, dk, dv) * 0.1).astype(np.float32)
+    S_rec = S.copy()
+    want = np.stack([gated_delta_rule_step(q[t], k[t], v[t], a[t], b[t], dt_bias, a_log, S_rec) for t in range(T)])
+    for h in range(nv):
+        kh = h * nk // nv
+        qn = q[:, kh] / np.sqrt((q[:, kh] ** 2).sum(-1, keepdims=True) + 1e-12) / np.sqrt(dk)
+        kn = k[:, kh] / np.sqrt((k[:, kh] ** 2).sum(-1, keepdims=True) + 1e-12)
+        x = a[:, h] + dt_bias[h]
+        g = -np.exp(a_log[h]) * np.where(x > 20, x, np.log1p(np.exp(x)))
+        beta = 1 / (1 + np.exp(-b[:, h]))
+        for chunk in (64, 37):
+            O, SC = gated_delta_rule_chunkwise(qn, kn, v[:, h], g, beta, S[h], chunk=chunk)
+            np.testing.assert_allclose(O, want[:, h], rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(SC, S_rec[h], rtol=2e-4, atol=2e-5)
