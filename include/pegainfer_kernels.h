@@ -302,6 +302,40 @@ int pk_b200_decode_attention_fused_prefetch(
 /* Grid (row slices) pk_b200_gemv_fused / gemm_cuda(N <= 4) uses for M output rows with epilogue `epi`. */
 int pk_b200_gemv_grid(int M, int epi);
 
+/* ---- Qwen3.5 hybrid-layer ops (next scope row; ffi.rs:181-226,981-1039) --------
+ * Memory-bound pieces of the gated-delta-net / gated HD-256 attention layers behind the reference's names
+ * (csrc/{flashinfer_norm,norm,conv1d,gated_delta_rule,prefill_attention_hd256}.cu).  HD-256 attention and the
+ * chunk-wise prefill of the delta rule are not provided yet.  Arithmetic: oracle/qwen35_oracle.py. */
+void rms_norm_batched_offset_cuda(const pk_bf16* x, const pk_bf16* weight, pk_bf16* out, int hidden_dim,
+                                  int seq_len, float eps, pk_stream stream); /* out = x*rsqrt(mean+eps)*(1+w) */
+void rms_norm_offset_cuda(const pk_bf16* x, const pk_bf16* weight, pk_bf16* out, int n, float eps,
+                          pk_stream stream);
+void rms_norm_gated_cuda(const pk_bf16* x, const float* weight, const pk_bf16* gate, pk_bf16* out,
+                         int num_heads, int head_dim, float eps, pk_stream stream);
+void gated_delta_rule_decode_cuda(const pk_bf16* qkv, const pk_bf16* b_proj, const pk_bf16* a_proj,
+                                  const pk_bf16* dt_bias, const float* A_log, float* state,
+                                  pk_bf16* output, int num_key_heads, int num_value_heads, int key_dim,
+                                  int val_dim, pk_stream stream); /* key_dim == val_dim == 128 */
+void conv1d_prefill_cuda(const pk_bf16* x_seq, const pk_bf16* conv_weight, pk_bf16* conv_state,
+                         pk_bf16* out_seq, int num_channels, int seq_len, int kernel_size,
+                         pk_stream stream);
+void prefill_attention_hd256_prep_cuda(const pk_bf16* q_full_batch, const pk_bf16* k_batch,
+                                       const pk_bf16* v_batch, const pk_bf16* q_norm_weight,
+                                       const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+                                       const pk_bf16* sin_cache, pk_bf16* q_batch_out, pk_bf16* k_cache,
+                                       pk_bf16* v_cache, int num_q_heads, int num_kv_heads, int seq_len,
+                                       const int* start_pos_ptr, int rotary_dim, float rms_eps,
+                                       int max_seq_len, pk_stream stream);
+void attention_gate_batch_hd256_cuda(const pk_bf16* q_full_batch, pk_bf16* attn_out, int num_q_heads,
+                                     int seq_len, pk_stream stream);
+void qk_norm_partial_rope_batched_decode_hd256_cuda(const pk_bf16* q_full_batch, pk_bf16* k_batch,
+                                                    const pk_bf16* q_norm_weight,
+                                                    const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,
+                                                    const pk_bf16* sin_cache, const int* positions,
+                                                    pk_bf16* q_batch_out, int num_q_heads, int num_kv_heads,
+                                                    int batch_size, int rotary_dim, float rms_eps,
+                                                    pk_stream stream);
+
 /* ---- TP all-reduce hook (pegainfer-qwen3-4b/src/weights.rs:396-405) ----------
  * One-shot all-reduce over NVLink peer memory: every rank owns a symmetric staging
  * buffer; peers' buffers are mapped (cudaIpc / peer access).  In-place SUM over

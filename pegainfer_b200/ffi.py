@@ -61,6 +61,19 @@ SIGNATURES = {
     "gpu_sample_flashinfer_cuda": (None, [vp, vp, vp, vp, i32, f32, i32, f32, C.c_uint64, vp]),
 }
 
+# Qwen3.5 hybrid-layer ops (ffi.rs:181-226,981-1039): present in our library and in the reference's full build, but not
+# in the Qwen3-only oracle/_ref library -> typed only when the symbol exists
+QWEN35_SIGNATURES = {
+    "rms_norm_batched_offset_cuda": (None, [vp, vp, vp, i32, i32, f32, vp]),
+    "rms_norm_offset_cuda": (None, [vp, vp, vp, i32, f32, vp]),
+    "rms_norm_gated_cuda": (None, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "gated_delta_rule_decode_cuda": (None, [vp] * 7 + [i32] * 4 + [vp]),
+    "conv1d_prefill_cuda": (None, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "prefill_attention_hd256_prep_cuda": (None, [vp] * 10 + [i32, i32, i32, vp, i32, f32, i32, vp]),
+    "attention_gate_batch_hd256_cuda": (None, [vp, vp, i32, i32, vp]),
+    "qk_norm_partial_rope_batched_decode_hd256_cuda": (None, [vp] * 8 + [i32, i32, i32, i32, f32, vp]),
+}
+
 # B200 extensions (absent from the reference's library)
 EXT_SIGNATURES = {
     "pk_b200_version": (C.c_char_p, []),
@@ -103,6 +116,7 @@ def load(path: str | None = None, extensions: bool = True) -> C.CDLL:
     sigs = dict(SIGNATURES)
     if extensions:
         sigs.update(EXT_SIGNATURES)
+        sigs.update(QWEN35_SIGNATURES)
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_ctypes_table_matches_header(built):
     from pegainfer_b200 import ffi
-    table = set(ffi.SIGNATURES) | set(ffi.EXT_SIGNATURES)
+    table = set(ffi.SIGNATURES) | set(ffi.EXT_SIGNATURES) | set(ffi.QWEN35_SIGNATURES)
     assert set(declared_symbols()) == table
     lib = ffi.load(built)  # dlopen + every symbol typed; no launches
     assert b"sm_100a" in lib.pk_b200_version()
