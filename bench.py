@@ -15,6 +15,7 @@ Keys of the JSON line (see the task contract):
             fed back on the device, no host sync inside the timed region; CUDA events on the stream)
   e2e       the same metric through the public API with HOST token ids: per step one H2D metadata copy
             from pinned memory, the graph launch, a 4-byte D2H of the sampled token and a stream sync
+  ttft_tensor  TTFT against the tensor roofline: prompt GEMM + causal attention flops / TTFT vs the measured sustained bf16 peak
   roofline  the dominant kernel (the HBM-streaming decode GEMV): algorithmic weight bytes per token /
             CUDA-event time of the token's 145 GEMV launches, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (port of the reference forward) timed on the host cores, bounded sample
@@ -57,6 +58,26 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def prefill_tensor_summary(cfg, prompt_len, ttft_ms, world):
+    """TTFT against the tensor roofline: dense GEMM flops of the prompt + causal attention + one lm_head row,
+    per GPU, over the measured TTFT (which also holds the host-side planning and the first sampling)."""
+    try:
+        h, i, l, v = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size
+        per_tok = 2.0 * l * (h * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.q_dim * h + 3 * h * i)
+        attn = 4.0 * cfg.num_attention_heads * cfg.head_dim * prompt_len * (prompt_len + 1) / 2 * l
+        flop = (per_tok * prompt_len + attn) / world + 2.0 * h * v
+        peak, src = 1416.7, "fallback"
+        pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pth):
+            d = json.load(open(pth))
+            peak, src = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", peak))), "measured (MEASURED_PEAKS.json, sustained)"
+        ach = flop / (ttft_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "flop_per_gpu": flop, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": src, "note": "end-to-end TTFT, not kernel time"}
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -310,6 +331,9 @@ def run_ours(args, cfg, rank, world, dist):
                                 "note": "whole decode step per GPU (weights + KV bytes / device time); per-kernel leg runs at N=1"}
         if cpu:
             line["cpu_baseline"] = cpu
+        pts = prefill_tensor_summary(cfg, prompt_len, ttft_ms, world)
+        if pts:
+            line["ttft_tensor"] = pts
         print(json.dumps(line), flush=True)
     model.close()
 
