@@ -7,19 +7,19 @@ Attention: the reference's own case (1 layer, nq 32, nkv 8, hd 128, page 16, bs 
 4096*seq + 16 KiB, seq in {1, 128, 1024, 4096}.  When oracle/_ref/libkernels_ref.so is present the reference's own
 kernels (cuBLAS GEMV, FlashInfer decode) are timed beside ours under the same protocol.
 
-Prints one JSON object; `python tools/bench_decode_micro.py > gpurun_out/micro.json`.
+Prints one JSON object; `python tests/tools/bench_decode_micro.py > gpurun_out/micro.json`.
 """
 import json
 import math
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
 
 from pegainfer_b200 import ffi  # noqa: E402
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ITERS = int(os.environ.get("MICRO_ITERS", "32"))
 torch.zeros(1, device="cuda")
 st = torch.cuda.current_stream().cuda_stream

@@ -1,6 +1,6 @@
 """Bring-up / regression check of the tcgen05 prefill attention kernel against the CPU oracle, one process per run.
 
-    python tools/check_prefill_tc.py [case ...]     cases: small ragged offset mid long batch (default: all)
+    python tests/tools/check_prefill_tc.py [case ...]     cases: small ragged offset mid long batch (default: all)
 
 Prints per case the max error in bf16 ulps (floor = max|want| / 32) and a timing for the long case.
 """
@@ -8,7 +8,7 @@ import math
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

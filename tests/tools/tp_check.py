@@ -1,13 +1,13 @@
 """Multi-GPU check under torchrun: (1) the one-shot NVLink all-reduce (plain and fused with add+RMSNorm)
 against torch / the CPU oracle, (2) Qwen3 TP-N prefill + decode logits against the CPU oracle's TP-N model.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/tp_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tools/tp_check.py
 """
 import ctypes as C
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

@@ -17,7 +17,7 @@ tp)
   port=29600
   for proto in flag ll; do for fused in 0 1; do
     port=$((port + 1))
-    PK_TP_PROTO=$proto PK_TP_FUSED=$fused timeout 150 $TR --master-port $port tools/tp_check.py 2>&1 | grep -E "TP_CHECK|MISMATCH" | sed "s/^/proto=$proto fused=$fused /"
+    PK_TP_PROTO=$proto PK_TP_FUSED=$fused timeout 150 $TR --master-port $port tests/tools/tp_check.py 2>&1 | grep -E "TP_CHECK|MISMATCH" | sed "s/^/proto=$proto fused=$fused /"
     port=$((port + 1))
     PK_TP_PROTO=$proto PK_TP_FUSED=$fused timeout 200 $TR --master-port $port bench.py --gpus $n --steps 128 --warmup 8 2>/dev/null |
       python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('proto=$proto fused=$fused tok/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3))"
