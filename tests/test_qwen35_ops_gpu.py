@@ -151,3 +151,42 @@ def test_hd256_prep_gate_and_decode_prep(lib):
                           floor=2 ** -6, what="q decode prep")
         assert_bf16_close(bits(k2[t]), O.f32_to_bf16(_norm_rope_ref(vals(k[t]), vals(kw), cos, sin, int(pos[t]), rd, 1e-6)), 2,
                           floor=2 ** -6, what="k decode prep")
+
+
+@pytest.mark.parametrize("seq_lens", [[1], [100], [700, 33]])
+def test_paged_attention_decode_hd256(lib, seq_lens):
+    nq, nkv, hd, bs, L = 16, 4, 256, len(seq_lens), 2
+    rng = np.random.RandomState(7)
+    need = [-(-s // 16) for s in seq_lens]
+    ids = rng.permutation(np.arange(1, sum(need) + 3))
+    pi, ip, lpl, off = [], [0], [], 0
+    for s, n in zip(seq_lens, need):
+        pi += ids[off:off + n].tolist(); off += n
+        ip.append(len(pi)); lpl.append(((s - 1) % 16) + 1)
+    block = 16 * nkv * hd                    # one K (or V) block of a page
+    layer_stride, page_stride = 2 * block, L * 2 * block
+    layer = 1
+    k_off, v_off = layer * layer_stride, layer * layer_stride + block
+    kv = rnd(((sum(need) + 4) * page_stride,), 30)
+    q = rnd((bs, nq, hd), 31)
+    kv_d, q_d = kv.cuda(), q.cuda()
+    out = torch.zeros((bs, nq, hd), dtype=torch.bfloat16, device="cuda")
+    dv = lambda a: torch.tensor(np.asarray(a, np.int32), device="cuda")
+    pi_d, ip_d, lpl_d, req_d, z_d = dv(pi), dv(ip), dv(lpl), dv(np.arange(bs)), dv(np.zeros(bs))
+    sm = 1 / math.sqrt(hd)
+    rc = lib.paged_attention_decode_cuda_hd256(q_d.data_ptr(), out.data_ptr(), kv_d.data_ptr(), k_off, v_off, pi_d.data_ptr(), ip_d.data_ptr(),
+                                               lpl_d.data_ptr(), req_d.data_ptr(), z_d.data_ptr(), z_d.data_ptr(), nq, nkv, hd, 16, bs,
+                                               page_stride, sm, st())
+    assert rc == 0
+    torch.cuda.synchronize()
+    kvv, qv = vals(kv), vals(q)
+    want = np.zeros((bs, nq, hd), np.float32)
+    for b, s in enumerate(seq_lens):
+        pages = pi[ip[b]:ip[b + 1]]
+        K = np.stack([kvv[pages[t // 16] * page_stride + k_off + (t % 16) * nkv * hd:][:nkv * hd].reshape(nkv, hd) for t in range(s)])
+        V = np.stack([kvv[pages[t // 16] * page_stride + v_off + (t % 16) * nkv * hd:][:nkv * hd].reshape(nkv, hd) for t in range(s)])
+        for h in range(nq):
+            sc = (K[:, h // 4] @ qv[b, h]).astype(np.float32) * np.float32(sm)
+            p = np.exp(sc - sc.max(), dtype=np.float32)
+            want[b, h] = (p @ V[:, h // 4]) / p.sum(dtype=np.float32)
+    assert_bf16_close(bits(out), O.f32_to_bf16(want), 3, floor=float(np.abs(want).max()) / 32, what="hd256 decode attention")
