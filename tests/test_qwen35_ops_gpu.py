@@ -190,3 +190,13 @@ def test_paged_attention_decode_hd256(lib, seq_lens):
             p = np.exp(sc - sc.max(), dtype=np.float32)
             want[b, h] = (p @ V[:, h // 4]) / p.sum(dtype=np.float32)
     assert_bf16_close(bits(out), O.f32_to_bf16(want), 3, floor=float(np.abs(want).max()) / 32, what="hd256 decode attention")
+
+
+def test_hybrid_model_bringup_matches_oracle(lib):
+    """End to end through the C ABI (tests/tools/qwen35_bringup.py): 24 teacher-forced steps of a tiny hybrid model."""
+    import importlib.util
+    p = os.path.join(os.path.dirname(__file__), "tools", "qwen35_bringup.py")
+    spec = importlib.util.spec_from_file_location("qwen35_bringup", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run()
