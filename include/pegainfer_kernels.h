@@ -316,6 +316,12 @@ void gated_delta_rule_decode_cuda(const pk_bf16* qkv, const pk_bf16* b_proj, con
                                   const pk_bf16* dt_bias, const float* A_log, float* state,
                                   pk_bf16* output, int num_key_heads, int num_value_heads, int key_dim,
                                   int val_dim, pk_stream stream); /* key_dim == val_dim == 128 */
+/* B200 extension: the same recurrence over a whole sequence (qkv_seq [T, 2*nk*128 + nv*128], b_seq / a_seq [T, nv],
+ * out_seq [T, nv*128]) with the state held in registers -- correctness-first prefill until the chunk-wise kernel exists. */
+int pk_b200_gated_delta_rule_prefill_recurrent(const pk_bf16* qkv_seq, const pk_bf16* b_seq, const pk_bf16* a_seq,
+                                               const pk_bf16* dt_bias, const float* A_log, float* state,
+                                               pk_bf16* out_seq, int num_key_heads, int num_value_heads,
+                                               int key_dim, int val_dim, int seq_len, pk_stream stream);
 void conv1d_prefill_cuda(const pk_bf16* x_seq, const pk_bf16* conv_weight, pk_bf16* conv_state,
                          pk_bf16* out_seq, int num_channels, int seq_len, int kernel_size,
                          pk_stream stream);

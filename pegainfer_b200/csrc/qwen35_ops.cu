@@ -142,6 +142,72 @@ gated_delta_rule_decode_kernel(const bf16* __restrict__ qkv, const bf16* __restr
   if (sl == 0) output[(size_t)vh * GV + col] = f2bf(part[0][col] + part[1][col] + part[2][col] + part[3][col]);
 }
 
+// Sequence form of the same recurrence (our extension, the correctness-first prefill until the chunk-wise tensor-core
+// kernel of oracle/qwen35_chunkwise.py exists): one CTA per value head walks the T tokens with the 128 x 128 fp32 state
+// held in REGISTERS the whole time (32 elements per thread), so the state costs one HBM read and one write per call and
+// each token only streams its q/k/v rows.  Latency-bound (~4 block barriers per token), not a roofline kernel.
+__global__ void __launch_bounds__(GV * GS)
+gated_delta_rule_seq_kernel(const bf16* __restrict__ qkv_seq, const bf16* __restrict__ b_seq, const bf16* __restrict__ a_seq,
+                            const bf16* __restrict__ dt_bias, const float* __restrict__ a_log, float* __restrict__ state,
+                            bf16* __restrict__ out_seq, int nk, int nv, int T) {
+  __shared__ float sq[GK], sk[GK], part[GS][GV], red[40];
+  __shared__ float s_decay, s_beta;
+  const int vh = blockIdx.x, col = threadIdx.x & (GV - 1), sl = threadIdx.x >> 7;
+  const int kh = vh * nk / nv;
+  const int qkv_dim = 2 * nk * GK + nv * GV;
+  pdl_wait();
+  float* st = state + ((size_t)vh * GK + (size_t)sl * GJ) * GV + col;
+  float s[GJ];
+#pragma unroll
+  for (int j = 0; j < GJ; ++j) s[j] = st[(size_t)j * GV];
+  const float bias = bf2f(dt_bias[vh]), neg_exp_a = -expf(a_log[vh]);
+  for (int t = 0; t < T; ++t) {
+    const bf16* row = qkv_seq + (size_t)t * qkv_dim;
+    float qv = 0.f, kv = 0.f;
+    if (sl == 0) {
+      qv = bf2f(row[(size_t)kh * GK + col]);
+      kv = bf2f(row[(size_t)nk * GK + (size_t)kh * GK + col]);
+    }
+    const float qn = block_sum(qv * qv, red);
+    const float kn = block_sum(kv * kv, red);
+    if (sl == 0) {
+      sq[col] = qv * rsqrtf(qn + 1e-12f) * rsqrtf((float)GK);
+      sk[col] = kv * rsqrtf(kn + 1e-12f);
+    }
+    if (threadIdx.x == 0) {
+      const float x = bf2f(a_seq[(size_t)t * nv + vh]) + bias;
+      const float sp = x > 20.0f ? x : logf(1.0f + expf(x));
+      s_decay = expf(neg_exp_a * sp);
+      s_beta = 1.0f / (1.0f + expf(-bf2f(b_seq[(size_t)t * nv + vh])));
+    }
+    __syncthreads();
+    const float decay = s_decay, beta = s_beta;
+    const float vv = bf2f(row[(size_t)2 * nk * GK + (size_t)vh * GV + col]);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      s[j] *= decay;
+      acc = fmaf(s[j], sk[sl * GJ + j], acc);
+    }
+    part[sl][col] = acc;
+    __syncthreads();
+    const float delta = (vv - (part[0][col] + part[1][col] + part[2][col] + part[3][col])) * beta;
+    __syncthreads();
+    acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      s[j] = fmaf(delta, sk[sl * GJ + j], s[j]);
+      acc = fmaf(s[j], sq[sl * GJ + j], acc);
+    }
+    part[sl][col] = acc;
+    __syncthreads();
+    if (sl == 0) out_seq[(size_t)t * nv * GV + (size_t)vh * GV + col] = f2bf(part[0][col] + part[1][col] + part[2][col] + part[3][col]);
+    // the next token's block_sum starts with a barrier, which also protects sq / sk / part
+  }
+#pragma unroll
+  for (int j = 0; j < GJ; ++j) st[(size_t)j * GV] = s[j];
+}
+
 // ---------------------------------------------------------------- HD-256 QK prep: prefill_attention_hd256.cu:7-113,176-262
 // One warp per (head, token): lane owns 8 consecutive dims (one 16-byte vector), so the per-head RMS is a warp
 // reduction and the RoPE partner (dim +- rotary_dim/2) sits rotary_dim/16 lanes away -- no shared memory, no barrier.
@@ -271,6 +337,15 @@ void gated_delta_rule_decode_cuda(const pk_bf16* qkv, const pk_bf16* b_proj, con
   if (key_dim != GK || val_dim != GV || num_value_heads <= 0 || num_key_heads <= 0) return;  // the reference's fixed 128 x 128 heads
   launch(gated_delta_rule_decode_kernel, dim3(num_value_heads), dim3(GV * GS), 0, stream, true, (const bf16*)qkv, (const bf16*)b_proj,
          (const bf16*)a_proj, (const bf16*)dt_bias, A_log, state, (bf16*)output, num_key_heads, num_value_heads);
+}
+int pk_b200_gated_delta_rule_prefill_recurrent(const pk_bf16* qkv_seq, const pk_bf16* b_seq, const pk_bf16* a_seq, const pk_bf16* dt_bias,
+                                               const float* A_log, float* state, pk_bf16* out_seq, int num_key_heads,
+                                               int num_value_heads, int key_dim, int val_dim, int seq_len, pk_stream stream) {
+  if (key_dim != GK || val_dim != GV || num_value_heads <= 0 || num_key_heads <= 0) return -1;
+  if (seq_len <= 0) return 0;
+  return (int)launch(gated_delta_rule_seq_kernel, dim3(num_value_heads), dim3(GV * GS), 0, stream, true, (const bf16*)qkv_seq,
+                     (const bf16*)b_seq, (const bf16*)a_seq, (const bf16*)dt_bias, A_log, state, (bf16*)out_seq, num_key_heads,
+                     num_value_heads, seq_len);
 }
 void prefill_attention_hd256_prep_cuda(const pk_bf16* q_full_batch, const pk_bf16* k_batch, const pk_bf16* v_batch,
                                        const pk_bf16* q_norm_weight, const pk_bf16* k_norm_weight, const pk_bf16* cos_cache,

@@ -69,6 +69,7 @@ QWEN35_SIGNATURES = {
     "rms_norm_gated_cuda": (None, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "gated_delta_rule_decode_cuda": (None, [vp] * 7 + [i32] * 4 + [vp]),
     "conv1d_prefill_cuda": (None, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "pk_b200_gated_delta_rule_prefill_recurrent": (i32, [vp] * 7 + [i32] * 5 + [vp]),
     "prefill_attention_hd256_prep_cuda": (None, [vp] * 10 + [i32, i32, i32, vp, i32, f32, i32, vp]),
     "attention_gate_batch_hd256_cuda": (None, [vp, vp, i32, i32, vp]),
     "qk_norm_partial_rope_batched_decode_hd256_cuda": (None, [vp] * 8 + [i32, i32, i32, i32, f32, vp]),

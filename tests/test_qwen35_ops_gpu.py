@@ -200,3 +200,25 @@ def test_hybrid_model_bringup_matches_oracle(lib):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run()
+
+
+def test_gated_delta_rule_prefill_recurrent(lib):
+    nk, nv, dk, dv, T = 16, 32, 128, 128, 37
+    g = torch.Generator().manual_seed(14)
+    qkv = rnd((T, 2 * nk * dk + nv * dv), 15)
+    a, b, dtb = rnd((T, nv), 16), rnd((T, nv), 17), rnd((nv,), 18, 0.5)
+    a_log = torch.randn(nv, generator=g) * 0.5
+    S = (torch.randn((nv, dk, dv), generator=g) * 0.1).float()
+    qkv_d, a_d, b_d, dtb_d, alog_d, Sd = qkv.cuda(), a.cuda(), b.cuda(), dtb.cuda(), a_log.cuda(), S.cuda()
+    out = torch.empty((T, nv * dv), dtype=torch.bfloat16, device="cuda")
+    rc = lib.pk_b200_gated_delta_rule_prefill_recurrent(qkv_d.data_ptr(), b_d.data_ptr(), a_d.data_ptr(), dtb_d.data_ptr(), alog_d.data_ptr(),
+                                                        Sd.data_ptr(), out.data_ptr(), nk, nv, dk, dv, T, st())
+    assert rc == 0
+    torch.cuda.synchronize()
+    qv, av, bv = vals(qkv), vals(a), vals(b)
+    Sw = S.numpy().copy()
+    want = np.stack([gated_delta_rule_step(qv[t, :nk * dk].reshape(nk, dk), qv[t, nk * dk:2 * nk * dk].reshape(nk, dk),
+                                           qv[t, 2 * nk * dk:].reshape(nv, dv), av[t], bv[t], vals(dtb), a_log.numpy(), Sw).reshape(-1)
+                     for t in range(T)])
+    assert_bf16_close(bits(out), O.f32_to_bf16(want), 2, floor=float(np.abs(want).max()) / 64, what="gdr sequence out")
+    np.testing.assert_allclose(Sd.cpu().numpy(), Sw, rtol=2e-4, atol=2e-5)
