@@ -4,23 +4,32 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N = 1 : BASELINE config[1] -- Qwen3-4B bf16, 2048-token prefill + decode at ctx 2048.., CUDA Graph on,
-        single request.  A "step" is one decode step (one generated token).
+        single request.  A "step" is one decode step (one generated token).  The same line also carries
+        BASELINE config[0] (128-token prompt / 64-token decode: `config1`), the Qwen3-8B single-GPU point of
+        config[2] (`tp_base`) and the reference's own CUDA kernels under the same host (`gpu_reference`).
 N > 1 : BASELINE config[2] -- Qwen3-8B bf16, tensor parallel over N ranks (one process per GPU,
-        NVLink peer-memory all-reduce), 128-token prompt, decode steps.  scaling = "strong".
-Random-init weights of the exact architecture (N(0, 0.02), seed 0) and synthetic prompt ids
-((i % 1000) + 100, bench_serving.rs:761-763); there is no network for checkpoints.
+        NVLink peer-memory all-reduce), 128-token prompt, decode steps.  scaling = "strong"; the line carries
+        `tp1` = the same model / prompt / steps on ONE GPU measured in the same run (rank 0's GPU), so a
+        strong-scaling ratio can be formed on one model.
+Checkpoint: random-init weights of the exact architecture generated ON THE CPU (N(0, 0.02), seed 0,
+pegainfer_b200/synthetic.py) -- the checkpoint the parity tests and the committed oracle fixtures use -- and
+synthetic prompt ids ((i % 1000) + 100, bench_serving.rs:761-763); there is no network for checkpoints.
 
 Keys of the JSON line (see the task contract):
   value     decode tok/s with inputs resident in HBM (per-step metadata pre-staged on the device, token
             fed back on the device, no host sync inside the timed region; CUDA events on the stream)
   e2e       the same metric through the public API with HOST token ids: per step one H2D metadata copy
             from pinned memory, the graph launch, a 4-byte D2H of the sampled token and a stream sync
+  parity    the benchmarked model checked against the CPU oracle's committed fixture for this configuration
+            (tests/golden/parity_*.npz: prefill + 8 teacher-forced decode steps, SURVEY 8c rule) BEFORE timing
   ttft_tensor  TTFT against the tensor roofline: prompt GEMM + causal attention flops / TTFT vs the measured sustained bf16 peak
   roofline  the dominant kernel (the HBM-streaming decode GEMV): algorithmic weight bytes per token /
-            CUDA-event time of the token's 145 GEMV launches, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (port of the reference forward) timed on the host cores, bounded sample
+            CUDA-event time of the token's 145 GEMV launches, vs MEASURED_PEAKS.json hbm_gbs; `traffic` = measured
+            dram bytes per launch from the committed ncu pass (profiles/gemv_traffic.json, per shape incl. lm_head)
+  cpu_baseline  the CPU oracle (port of the reference forward) timed on the host cores at the GPU arm's context
+            length, OpenMP thread count set and reported, three repeats
 `--impl reference` times that CPU port alone (the reference has no CPU path of its own and its Rust
-host cannot be built here; oracle/_ref holds its CUDA kernels, which are GPU code, not a CPU arm).
+host cannot be built here; oracle/_ref holds its CUDA kernels, which are GPU code: they are the `gpu_reference` leg).
 """
 from __future__ import annotations
 
@@ -33,8 +42,16 @@ import sys
 import threading
 import time
 
+# The CPU arm's OpenMP runtime reads these when the oracle library is first loaded: one thread per hardware thread,
+# bound in place (reproducible timings on a 2-socket host).  torchrun's OMP_NUM_THREADS=1 is overridden explicitly
+# through orc_set_num_threads.
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "threads")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libkernels_ref.so")
+PARITY_TOL_ULP = 8
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -58,6 +75,13 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def prefill_tensor_summary(cfg, prompt_len, ttft_ms, world):
@@ -121,52 +145,71 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_oracle(cfg, weights_np, num_pages):
+# ------------------------------------------------------------------------------------ CPU arm (the oracle port)
+def make_oracle(cfg, weights_np, num_pages, tp_world=1):
     from oracle import qwen3_oracle as O
     oc = O.OracleConfig(cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.num_attention_heads,
                         cfg.num_key_value_heads, cfg.head_dim, cfg.vocab_size, cfg.rms_norm_eps, cfg.rope_theta,
                         cfg.tie_word_embeddings)
-    return O, O.OracleQwen3(oc, weights_np, num_pages=num_pages)
+    return O, O.OracleQwen3(oc, weights_np, tp_world=tp_world, num_pages=num_pages)
 
 
-def cpu_decode_rate(cfg, weights_np, steps, budget_s, ctx=16):
-    """Time `steps` full-depth greedy decode steps of the CPU oracle (OpenMP, all host cores).
-    Context is `ctx` tokens (the weight stream is > 96 % of the bytes at the metric's ctx anyway)."""
+def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
+    """Greedy decode steps of the CPU oracle at context `ctx` (the GPU arm's), all host threads.
+
+    The context is created with OracleQwen3.fill_context (random K/V, no 2048-token CPU prefill: decode timing does
+    not depend on the cached values); weights are re-homed for NUMA locality (rehome_weights); the OpenMP team size
+    is set explicitly and read back.  `repeats` timed runs of n steps each -> (median tok/s, runs, n, threads)."""
     from pegainfer_b200.synthetic import synthetic_prompt
-    O, orc = make_oracle(cfg, weights_np, num_pages=(ctx + steps + 2) // 16 + 4)  # whole run fits: prompt + warm-up + steps
+    threads = host_threads()
+    O, orc = make_oracle(cfg, weights_np, num_pages=(ctx + 64) // 16 + 8)
+    threads = O.set_num_threads(threads)
+    orc.rehome_weights()
     kv = orc.alloc_kv()
-    lg = orc.prefill([synthetic_prompt(ctx)], [kv])[0]
-    tok = O.argmax(lg)
-    t_warm = time.perf_counter()
-    tok = O.argmax(orc.decode([tok], [kv])[0])  # warm-up step
-    t_step = time.perf_counter() - t_warm
-    n = max(1, min(steps, int(budget_s / max(t_step, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        tok = O.argmax(orc.decode([tok], [kv])[0])
-    dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    orc.fill_context(kv, ctx)
+    tok = synthetic_prompt(1)[0]
+    tok = O.argmax(orc.decode([tok], [kv])[0])  # warm-up (first touch of the KV pages, thread team start)
+    t_w = time.perf_counter()
+    tok = O.argmax(orc.decode([tok], [kv])[0])
+    t_step = time.perf_counter() - t_w
+    n = max(2, min(16, int(budget_s / repeats / max(t_step, 1e-3))))
+    runs = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            tok = O.argmax(orc.decode([tok], [kv])[0])
+        runs.append(n / (time.perf_counter() - t0))
+    return statistics.median(runs), runs, n, threads, kv.seq_len
 
 
-# ------------------------------------------------------------------------------------ reference arm
+def cpu_arm_ctx(world):
+    return 2048 if world == 1 else 128
+
+
+def cpu_sample_text(cfg, n, runs, threads, ctx_end):
+    spread = (max(runs) - min(runs)) / statistics.median(runs)
+    return (f"{len(runs)} x {n} full-depth {cfg.name} greedy decode steps of the CPU oracle ending at ctx {ctx_end} (context "
+            f"pre-filled, no CPU prefill), bs 1; OpenMP {threads} threads (OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, "
+            f"OMP_PLACES={os.environ.get('OMP_PLACES')}), weights first-touched per thread; runs "
+            f"{[round(r, 2) for r in runs]} tok/s, spread {spread:.1%}")
+
+
 def run_reference(args, cfg, rank, world):
     """CPU port of the reference forward on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    import torch
     from pegainfer_b200.synthetic import random_weights, to_numpy_bits
-    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     w = to_numpy_bits(random_weights(cfg, seed=0, device="cpu"))
     gen_s = time.perf_counter() - t0
-    rate, n, dt = cpu_decode_rate(cfg, w, args.steps, budget_s=150.0)
-    sample = (f"{n} of the requested {args.steps} full-depth {cfg.name} greedy decode steps on the CPU oracle "
-              f"(ctx 17.., bs 1), OpenMP over {cores} host threads; weights generated on CPU in {gen_s:.0f}s")
+    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(world), budget_s=40.0)
+    sample = cpu_sample_text(cfg, n, runs, threads, ctx_end) + f"; weights generated on CPU in {gen_s:.0f}s"
     line = {"impl": "reference", "metric": "decode_tok_s", "value": rate, "unit": "tok/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": bench_workload_name(cfg, world)},
-            "cpu_baseline": {"value": rate, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample,
+                             "runs": runs},
             "e2e": {"value": rate, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -216,12 +259,63 @@ def make_tp_comm(rank, world, dist, max_tokens, hidden):
     return comm
 
 
+# ------------------------------------------------------------------------------------ parity against the fixtures
+def parity_check(model, cfg, prompt_len, world, rank, dist):
+    """Teacher-forced prefill + decode steps of the benchmarked model vs the committed oracle fixture (SURVEY 8c rule).
+    Every rank runs the model; rank 0 compares.  Returns a dict for the JSON line (None on other ranks)."""
+    import torch
+    from pegainfer_b200.synthetic import synthetic_prompt
+    from tests.golden import parity_fixture as F
+    path = F.fixture_path(cfg.name, prompt_len, world)
+    if not os.path.exists(path):
+        return {"checked": False, "why": f"no fixture {os.path.basename(path)}"} if rank == 0 else None
+    fx = F.Fixture(path)
+    kv = model.alloc_kv()
+    rows = [model.prefill([synthetic_prompt(prompt_len)], [kv])[0]]
+    for t in fx.tokens:
+        lg, _ = model.decode([t], [kv])
+        rows.append(lg[0])
+    model.drop_request(kv)
+    if rank != 0:
+        return None
+    worst, same, ok = 0.0, 0, True
+    for step, r in enumerate(rows):
+        good, info = fx.compare(step, r.detach().cpu().contiguous().view(torch.int16).numpy().view("uint16"), PARITY_TOL_ULP)
+        worst, same, ok = max(worst, info["err_ulp_rowmax"]), same + int(info["same_argmax"]), ok and good
+    return {"checked": True, "ok": ok, "fixture": os.path.relpath(path, ROOT), "steps": len(rows),
+            "worst_err_ulp_rowmax": round(worst, 3), "tol_ulp_rowmax": PARITY_TOL_ULP, "argmax_equal": f"{same}/{len(rows)}",
+            "rule": "teacher-forced; |dlogit| <= tol bf16 ulps at the row max on the top-256 + every 16th logit; arg-max "
+                    "equal unless the oracle's top-1/top-2 gap <= 2 tol"}
+
+
+def time_decode(model, prompt, K, W, barrier):
+    """(e2e_ms, burst_ms, ctx_lo): K public-API steps (host ids in/out) then K device-resident steps of one request."""
+    kv = model.alloc_kv()
+    tok = model.sample_greedy(model.prefill([prompt], [kv])[0])
+    for _ in range(W):
+        _, s = model.decode([tok], [kv], want_logits=False)
+        tok = s[0]
+    barrier()
+    e0 = model.event_record()
+    for _ in range(K):
+        _, s = model.decode([tok], [kv], want_logits=False)
+        tok = s[0]
+    e1 = model.event_record()
+    e2e_ms = model.event_elapsed_ms(e0, e1)
+    barrier()
+    _, burst_ms = model.decode_burst(kv, tok, K)
+    ctx_lo = len(prompt) + 1 + W + K
+    model.drop_request(kv)
+    barrier()
+    return e2e_ms, burst_ms, ctx_lo
+
+
 # ------------------------------------------------------------------------------------ our arm
 def run_ours(args, cfg, rank, world, dist):
     import torch
-    from pegainfer_b200.config import TensorParallelConfig
+    from pegainfer_b200.config import PRESETS, TensorParallelConfig
     from pegainfer_b200.model import ModelRuntimeConfig, Qwen3Model
-    from pegainfer_b200.synthetic import iter_random_weights, synthetic_prompt
+    from pegainfer_b200.synthetic import iter_random_weights, synthetic_prompt, weight_shapes
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -237,7 +331,31 @@ def run_ours(args, cfg, rank, world, dist):
                             device_ordinal=local_rank, fused=True, persistent=persistent, num_pages=pages,
                             max_batch=1, enable_pdl=True)
     t0 = time.perf_counter()
-    model = Qwen3Model(cfg, iter_random_weights(cfg, seed=0, device="cuda"), rt, tp_comm=tp_comm)
+    # ---- checkpoint: generated on the CPU (rank 0), the one the oracle fixtures were computed on ----
+    model = Qwen3Model(cfg, None, rt, tp_comm=tp_comm)
+    tp1_model = None
+    want_tp1 = world > 1 and rank == 0 and not args.no_tp_base
+    if want_tp1:
+        tp1_model = Qwen3Model(cfg, None, ModelRuntimeConfig(enable_cuda_graph=True, device_ordinal=local_rank, fused=True,
+                                                            num_pages=pages, max_batch=1, enable_pdl=True))
+    keep_cpu = {} if (world == 1 and rank == 0) else None
+    gen = iter_random_weights(cfg, seed=0, device="cpu") if rank == 0 else None
+    for name, shape in weight_shapes(cfg).items():
+        if rank == 0:
+            n2, t = next(gen)
+            assert n2 == name
+            if keep_cpu is not None:
+                keep_cpu[name] = t
+        if world > 1:
+            d = t.cuda() if rank == 0 else torch.empty(shape, dtype=torch.bfloat16, device="cuda")
+            dist.broadcast(d, 0)
+            t = d
+        model.load_tensor(name, t)
+        if tp1_model is not None:
+            tp1_model.load_tensor(name, t)
+    model.finalize()
+    if tp1_model is not None:
+        tp1_model.finalize()
     load_s = time.perf_counter() - t0
     prompt = synthetic_prompt(prompt_len)
 
@@ -246,6 +364,9 @@ def run_ours(args, cfg, rank, world, dist):
         if dist is not None:
             dist.barrier()
 
+    # ---- parity of the model being benchmarked (before any timing) ----
+    parity = parity_check(model, cfg, prompt_len, world, rank, dist)
+    parity1 = parity_check(model, cfg, 128, 1, rank, dist) if world == 1 else None
     # ---- warm-up: graph capture, allocator, clocks ----
     model.generate(prompt, 4)
     # ---- TTFT: prompt submit -> first token (host ids in, token out), median of 3 ----
@@ -257,25 +378,7 @@ def run_ours(args, cfg, rank, world, dist):
     ttft_ms = statistics.median(ttfts)
 
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
-    # ---- e2e: public API, host token ids, per-step H2D + D2H + sync ----
-    kv = model.alloc_kv()
-    tok = model.sample_greedy(model.prefill([prompt], [kv])[0])
-    for _ in range(W):
-        _, s = model.decode([tok], [kv], want_logits=False)
-        tok = s[0]
-    barrier()
-    e0 = model.event_record()
-    for _ in range(K):
-        _, s = model.decode([tok], [kv], want_logits=False)
-        tok = s[0]
-    e1 = model.event_record()
-    e2e_ms = model.event_elapsed_ms(e0, e1)
-    barrier()
-    # ---- device-resident: K more steps, metadata staged in HBM, token fed back on the device ----
-    burst_tokens, burst_ms = model.decode_burst(kv, tok, K)
-    ctx_lo = prompt_len + 1 + W + K
-    model.drop_request(kv)
-    barrier()
+    e2e_ms, burst_ms, ctx_lo = time_decode(model, prompt, K, W, barrier)
     clk = clocks.stop() if clocks else None
 
     def max_over_ranks(x):
@@ -287,6 +390,21 @@ def run_ours(args, cfg, rank, world, dist):
 
     e2e_ms, burst_ms, ttft_ms = max_over_ranks(e2e_ms), max_over_ranks(burst_ms), max_over_ranks(ttft_ms)
     launches_per_step = model.launches_per_step()
+
+    # ---- BASELINE config[0] in the same run: 128-token prompt, 64 generated tokens (1 prefill + 63 decode steps) ----
+    config1 = None
+    if world == 1:
+        p128 = synthetic_prompt(128)
+        model.generate(p128, 4)
+        t1 = [model.generate(p128, 1)[1] for _ in range(3)]
+        _, _, gaps = model.generate(p128, 64)
+        kvc = model.alloc_kv()
+        tokc = model.sample_greedy(model.prefill([p128], [kvc])[0])
+        _, b_ms = model.decode_burst(kvc, tokc, 63)
+        model.drop_request(kvc)
+        config1 = {"workload": "Qwen3-4B, 128-token prompt / 64-token greedy decode, bs 1 (BASELINE config 0)",
+                   "ttft_ms": statistics.median(t1), "decode_tok_s_e2e": len(gaps) / (sum(gaps) * 1e-3),
+                   "decode_tok_s": 63 / (b_ms * 1e-3), "decode_steps": 63, "parity": parity1}
 
     # ---- roofline of the dominant kernel (decode GEMV), live CUDA-event timing ----
     peak, peak_src = measured_peaks()
@@ -302,10 +420,32 @@ def run_ours(args, cfg, rank, world, dist):
     step_bytes = wbytes + kv_bytes_per_ctx_token(cfg, world) * (ctx_lo + K // 2)
     step_ms = burst_ms / K
     step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
+    meta_bytes = model.meta_bytes()
+    model.close()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_leg(cfg)
+    # ---- N > 1: the same model / prompt / steps on ONE GPU (rank 0), the base of the strong-scaling ratio ----
+    tp1 = None
+    if world > 1:
+        if tp1_model is not None:
+            tp1_model.generate(prompt, 4)
+            tt = statistics.median([tp1_model.generate(prompt, 1)[1] for _ in range(3)])
+            e1_ms, b1_ms, _ = time_decode(tp1_model, prompt, K, W, lambda: torch.cuda.synchronize())
+            tp1 = {"model": cfg.name, "value": K / (b1_ms * 1e-3), "unit": "tok/s", "e2e": K / (e1_ms * 1e-3), "ttft_ms": tt,
+                   "ms_per_step": b1_ms / K, "how": "same checkpoint, prompt and step count on rank 0's GPU alone, measured "
+                   "in this run after the TP measurement (other ranks idle)"}
+            tp1_model.close()
+        barrier()
+
+    # ---- N = 1 side legs ----
+    gpu_ref = tp_base = cpu = None
+    if world == 1 and rank == 0:
+        if not args.no_gpu_reference:
+            gpu_ref = gpu_reference_leg(cfg, keep_cpu, prompt, pages)
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_leg(cfg, keep_cpu)
+        keep_cpu = None
+        if not args.no_tp_base:
+            tp_base = tp_base_leg(PRESETS["qwen3-8b"], local_rank)
 
     if rank == 0:
         value = K / (burst_ms * 1e-3)
@@ -315,12 +455,13 @@ def run_ours(args, cfg, rank, world, dist):
                 "config": {"workload": bench_workload_name(cfg, world), "prompt_len": prompt_len,
                            "decode_ctx": [ctx_lo, ctx_lo + K], "l2": "inputs (weights 8-15 GB/token) >> 126 MB L2, no flush needed",
                            "parallelism": f"tp{world}", "cuda_graph": True, "pdl": True,
+                           "checkpoint": "random-init N(0, 0.02), seed 0, generated on the CPU (the oracle fixtures' checkpoint)",
                            "decode_impl": "persistent single-launch step" if persistent else "fused multi-kernel graph",
                            "launches_per_step": launches_per_step, "model_load_s": round(load_s, 1)},
                 "ttft_ms": ttft_ms, "ttft_prompt_len": prompt_len,
                 "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "tok/s", "ms_per_step": e2e_ms / K,
-                        "h2d_bytes_per_step": model.meta_bytes(), "d2h_bytes_per_step": 4},
-                "gpu_launches": launches_per_step * K,
+                        "h2d_bytes_per_step": meta_bytes, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches_per_step * K, "parity": parity,
                 "step_hbm": {"bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac_of_peak": step_gbs / peak},
                 "clocks": clk}
         if roof:
@@ -331,15 +472,23 @@ def run_ours(args, cfg, rank, world, dist):
                                 "note": "whole decode step per GPU (weights + KV bytes / device time); per-kernel leg runs at N=1"}
         if cpu:
             line["cpu_baseline"] = cpu
+        if config1:
+            line["config1"] = config1
+        if gpu_ref:
+            line["gpu_reference"] = gpu_ref
+        if tp_base:
+            line["tp_base"] = tp_base
+        if tp1:
+            line["tp1"] = tp1
+            line["speedup_vs_tp1"] = value / tp1["value"]
         pts = prefill_tensor_summary(cfg, prompt_len, ttft_ms, world)
         if pts:
             line["ttft_tensor"] = pts
         print(json.dumps(line), flush=True)
-    model.close()
 
 
 def profile_traffic():
-    """dram bytes per GEMV launch from the committed ncu summary, if present (profiles/)."""
+    """dram bytes per GEMV launch from the committed ncu pass, if present (profiles/gemv_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "gemv_traffic.json")
     try:
         return json.load(open(p))["dram_bytes_per_launch"]
@@ -347,15 +496,72 @@ def profile_traffic():
         return None
 
 
-def cpu_baseline_leg(cfg):
+def cpu_baseline_leg(cfg, weights_cpu):
+    from pegainfer_b200.synthetic import to_numpy_bits
+    w = to_numpy_bits(weights_cpu)
+    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(1), budget_s=24.0)
+    return {"value": rate, "unit": "tok/s", "cores": threads, "kind": "port", "runs": runs,
+            "sample": cpu_sample_text(cfg, n, runs, threads, ctx_end)}
+
+
+def gpu_reference_leg(cfg, weights_cpu, prompt, pages):
+    """The reference's OWN CUDA kernels (cuBLAS GEMV/GEMM + FlashInfer attention/norm/top-1, compiled from
+    /root/reference by oracle/Makefile into oracle/_ref) driven by the same C++ host through the identical C ABI, the
+    reference's op sequence, CUDA Graph on: the 'existing kernel to beat' on this box.  Reported baseline only."""
+    if not os.path.exists(REF_LIB):
+        return {"available": False, "why": "oracle/_ref/libkernels_ref.so not built (needs /root/reference at build time)"}
+    from pegainfer_b200.model import ModelRuntimeConfig, Qwen3Model
+    try:
+        m = Qwen3Model(cfg, weights_cpu, ModelRuntimeConfig(enable_cuda_graph=True, fused=False, num_pages=pages, max_batch=1,
+                                                            kernel_lib=REF_LIB))
+        m.generate(prompt, 4)
+        ttft = statistics.median([m.generate(prompt, 1)[1] for _ in range(3)])
+        kv = m.alloc_kv()
+        tok = m.sample_greedy(m.prefill([prompt], [kv])[0])
+        for _ in range(4):
+            tok = m.decode([tok], [kv], want_logits=False)[1][0]
+        e0 = m.event_record()
+        n = 64
+        for _ in range(n):
+            tok = m.decode([tok], [kv], want_logits=False)[1][0]
+        ms = m.event_elapsed_ms(e0, m.event_record())
+        p128 = prompt[:128]
+        m.generate(p128, 2)
+        ttft128 = statistics.median([m.generate(p128, 1)[1] for _ in range(3)])
+        m.close()
+        return {"available": True, "decode_tok_s": n / (ms * 1e-3), "ms_per_step": ms / n, "ttft_ms": ttft, "ttft_128_ms": ttft128,
+                "steps": n, "what": "reference kernels (cuBLAS + FlashInfer, sm_100 build of /root/reference/pegainfer-kernels/csrc) "
+                "under the same host and C ABI, reference op sequence (batch_decode.rs), split-KV decode attention, CUDA Graph; "
+                "timed through the public API (host token in/out per step)"}
+    except Exception as e:  # a baseline leg must never take the benchmark down
+        return {"available": False, "why": f"{type(e).__name__}: {e}"[:300]}
+
+
+def tp_base_leg(cfg8, device):
+    """Qwen3-8B on ONE GPU, 128-token prompt, 256 decode steps: the N=1 point of BASELINE config 2 ('1/2/4/8')."""
+    from pegainfer_b200.model import ModelRuntimeConfig, Qwen3Model
+    from pegainfer_b200.synthetic import iter_random_weights, synthetic_prompt
     import torch
-    from pegainfer_b200.synthetic import random_weights, to_numpy_bits
-    cores = os.cpu_count() or 1
-    w = to_numpy_bits(random_weights(cfg, seed=0, device="cpu"))
-    rate, n, dt = cpu_decode_rate(cfg, w, steps=64, budget_s=20.0)
-    return {"value": rate, "unit": "tok/s", "cores": cores, "kind": "port",
-            "sample": f"{n} full-depth {cfg.name} greedy decode steps ({dt:.1f} s) of the CPU oracle at ctx 17.., "
-                      f"OpenMP over {cores} host threads"}
+    try:
+        t0 = time.perf_counter()
+        K = 256
+        m = Qwen3Model(cfg8, iter_random_weights(cfg8, seed=0, device="cpu"),
+                       ModelRuntimeConfig(enable_cuda_graph=True, device_ordinal=device, fused=True, num_pages=96, max_batch=1))
+        load_s = time.perf_counter() - t0
+        prompt = synthetic_prompt(128)
+        par = parity_check(m, cfg8, 128, 1, 0, None)
+        m.generate(prompt, 4)
+        ttft = statistics.median([m.generate(prompt, 1)[1] for _ in range(3)])
+        e2e_ms, burst_ms, ctx_lo = time_decode(m, prompt, K, 8, lambda: torch.cuda.synchronize())
+        peak, _ = measured_peaks()
+        bytes_step = weight_bytes_per_token(cfg8, 1) + kv_bytes_per_ctx_token(cfg8, 1) * (ctx_lo + K // 2)
+        gbs = bytes_step / (burst_ms / K * 1e-3) / 1e9
+        m.close()
+        return {"model": cfg8.name, "n_gpus": 1, "value": K / (burst_ms * 1e-3), "unit": "tok/s", "e2e": K / (e2e_ms * 1e-3),
+                "ms_per_step": burst_ms / K, "ttft_ms": ttft, "prompt_len": 128, "steps": K, "parity": par,
+                "step_hbm_frac": gbs / peak, "model_load_s": round(load_s, 1)}
+    except Exception as e:
+        return {"available": False, "why": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -366,7 +572,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default=None, help="override: qwen3-4b | qwen3-8b | qwen3-small | qwen3-tiny")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-tp-base", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the side legs (cpu_baseline, gpu_reference, tp_base / tp1)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_gpu_reference = args.no_tp_base = True
     if args.warmup < 3:
         args.warmup = 3
     from pegainfer_b200.config import PRESETS

@@ -28,6 +28,18 @@
 
 #define ORC_API __attribute__((visibility("default")))
 
+/* ---- OpenMP control (bench.py's CPU arm states and pins its thread count; torchrun exports
+ * OMP_NUM_THREADS=1 to every rank, which must not silently turn the "all host cores" baseline into a
+ * single-threaded one) ----------------------------------------------------- */
+#ifdef _OPENMP
+#include <omp.h>
+ORC_API void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+ORC_API int orc_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+ORC_API void orc_set_num_threads(int n) { (void)n; }
+ORC_API int orc_get_max_threads(void) { return 1; }
+#endif
+
 /* ---- bf16 helpers: __float2bfloat16 is round-to-nearest-even ------------ */
 static inline float bf2f(uint16_t h) {
   uint32_t u = ((uint32_t)h) << 16;
@@ -49,6 +61,14 @@ ORC_API void orc_f32_to_bf16(const float* in, uint16_t* out, int64_t n) {
 }
 ORC_API void orc_bf16_to_f32(const uint16_t* in, float* out, int64_t n) {
   for (int64_t i = 0; i < n; ++i) out[i] = bf2f(in[i]);
+}
+
+/* Row-parallel copy with the SAME static row partition orc_gemm uses: the destination's pages are first touched by
+ * the thread that will stream those rows, so on a multi-socket host every thread reads local memory (bench.py's CPU
+ * arm re-homes the weight matrices with this; timing hygiene only, no arithmetic). */
+ORC_API void orc_spread_rows(uint16_t* dst, const uint16_t* src, int64_t rows, int64_t cols) {
+#pragma omp parallel for schedule(static)
+  for (int64_t m = 0; m < rows; ++m) memcpy(dst + m * cols, src + m * cols, (size_t)cols * 2);
 }
 
 /* fp32 dot product, 16 independent partial sums (vectorisable), fixed tree. */

@@ -65,6 +65,26 @@ def _p(a: np.ndarray | None, ty):
     return a.ctypes.data_as(ty)
 
 
+def set_num_threads(n: int) -> int:
+    """Pin the oracle's OpenMP team size (torchrun exports OMP_NUM_THREADS=1); returns the size in effect."""
+    lib().orc_set_num_threads(int(n))
+    return int(lib().orc_get_max_threads())
+
+
+def get_max_threads() -> int:
+    return int(lib().orc_get_max_threads())
+
+
+def spread_rows(a: np.ndarray) -> np.ndarray:
+    """Copy of a 2-D matrix whose pages are first touched with orc_gemm's static row partition (NUMA locality)."""
+    a = np.ascontiguousarray(a)
+    if a.ndim != 2:
+        return a
+    out = np.empty_like(a)
+    lib().orc_spread_rows(_p(out, _u16p), _p(a, _u16p), C.c_int64(a.shape[0]), C.c_int64(a.shape[1]))
+    return out
+
+
 # ---------------------------------------------------------------- bf16 helpers
 def f32_to_bf16(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -317,6 +337,29 @@ class OracleQwen3:
         self.free = list(range(num_pages - 1, 0, -1))
         self.sm_scale = 1.0 / math.sqrt(cfg.head_dim)
         self.last_attention_path = None
+
+    def rehome_weights(self):
+        """Timing hygiene for bench.py's CPU arm: re-home every streamed matrix with spread_rows (first touch by the
+        thread that reads it).  No arithmetic changes."""
+        tied = self.lm_head is self.embed
+        self.lm_head = spread_rows(self.lm_head)
+        if tied:
+            self.embed = self.lm_head
+        for rk in self.ranks:
+            for L in rk.layers:
+                for k in ("qkv", "gate_up", "o", "down"):
+                    L[k] = spread_rows(L[k])
+
+    def fill_context(self, kv: "OracleKv", tokens: int, seed: int = 0):
+        """Timing hygiene: give `kv` a context of `tokens` entries of small random K/V WITHOUT running a prefill (a
+        2048-token CPU prefill is ~16 TFLOP); decode timing at that context does not depend on the values."""
+        self._ensure(kv, tokens)
+        kv.seq_len = tokens
+        rng = np.random.default_rng(seed)
+        for rk in self.ranks:
+            for pg in kv.pages:
+                lo = pg * rk.page_stride
+                rk.kv[lo:lo + rk.page_stride] = rng.integers(0x3c00, 0x3c80, rk.page_stride, dtype=np.uint16)
 
     # -- paging --------------------------------------------------------------
     def alloc_kv(self) -> OracleKv:

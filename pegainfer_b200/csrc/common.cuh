@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/pegainfer_kernels.h"
 
@@ -45,6 +47,14 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// The reference's void entry points have no error channel: its Rust wrappers assert the shapes and panic.  A void
+// entry here that is handed a shape its kernel does not cover fails the same way -- loudly -- instead of returning
+// with the output untouched.
+[[noreturn]] inline void unsupported(const char* fn, const char* why) {
+  fprintf(stderr, "pegainfer_kernels_b200: %s: unsupported arguments (%s)\n", fn, why);
+  abort();
 }
 
 // ---- device helpers ----

@@ -472,13 +472,22 @@ static int pick_max_chunks(int bs, int nkv, int nq, size_t scratch_floats) {
 }
 
 
-static bool use_cluster_attention() {
+// PK_ATTN = tma (default: decode_attention_tma.cu) | cluster (round-1 LDG cluster kernel) | ticket (global-memory merge)
+static int attention_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PK_ATTN");
-    v = (e && strcmp(e, "ticket") == 0) ? 0 : 1;
+    v = (e && strcmp(e, "ticket") == 0) ? 0 : ((e && strcmp(e, "cluster") == 0) ? 1 : 2);
   }
-  return v == 1;
+  return v;
+}
+static bool use_cluster_attention() { return attention_impl() >= 1; }
+static int launch_cluster_or_tma(const ClusterAttnArgs& c, int nkv, int bs, cudaStream_t stream) {
+  if (attention_impl() == 2 && c.npf == 0) {
+    const int rc = launch_decode_attention_tma(c, nkv, bs, stream);
+    if (rc != -2) return rc;
+  }
+  return (int)launch_decode_attention_cluster(c, nkv, bs, stream);
 }
 
 // Extra cluster rows of the fused launch that only issue L2 prefetches (PK_PF_Y, default 8 -> 64 CTAs).
@@ -521,7 +530,7 @@ int paged_attention_decode_cuda(const pk_bf16* q, pk_bf16* output, const pk_bf16
     c.request_indices = request_indices;
     c.sm_scale_log2 = sm_scale * 1.44269504088896340736f;
     c.nq = num_qo_heads; c.nkv = num_kv_heads;
-    return (int)launch_decode_attention_cluster(c, num_kv_heads, batch_size, stream);
+    return launch_cluster_or_tma(c, num_kv_heads, batch_size, stream);
   }
   ThreadState& ts = tls();
   // scratch layout: [counters: bs*nkv ints, padded to 4 KB][fp32 partials]
@@ -599,7 +608,7 @@ static int decode_attention_fused_impl(
       c.pf[c.npf++] = PfSpan{static_cast<const uint8_t*>(sp.base), sp.rows, sp.row_bytes, sp.slices, sp.prefetch_rows};
     }
     c.pf_y = prefetch_cluster_rows();
-    return (int)launch_decode_attention_cluster(c, num_kv_heads, batch_size, stream);
+    return launch_cluster_or_tma(c, num_kv_heads, batch_size, stream);
   }
   DecodeAttnArgs a{};
   a.q = (const bf16*)q; a.out = (bf16*)output; a.kv = (bf16*)kv_data;

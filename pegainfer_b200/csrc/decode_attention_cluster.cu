@@ -45,6 +45,9 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, uint32_t r
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// split cluster barrier: arrive at entry, wait before the first remote store (every CTA of the cluster has started)
+__device__ __forceinline__ void cluster_arrive_open() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_open() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -119,6 +122,7 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
     }
     return;
   }
+  cluster_arrive_open();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int rank = (int)cluster_rank();
   // plain mode (the ABI's paged_attention_decode_cuda): q arrives normed + roped, the step's K/V row was appended
@@ -293,6 +297,7 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
         make_float4(bf16_lo(vr2.x), bf16_hi(vr2.x), bf16_lo(vr2.y), bf16_hi(vr2.y));
   }
   __syncthreads();
+  cluster_wait_open();
   const int nstates = inject ? C_WARPS + 1 : C_WARPS;
   const int t = threadIdx.x;
   if (t < CHD) {
@@ -330,7 +335,7 @@ decode_attention_cluster_kernel(const ClusterAttnArgs a) {
       dd = fmaf(c_d[r][h], w, dd);
       oo = fmaf(c_o[r][h][t], w, oo);
     }
-    a.out[((size_t)b * a.nq + kvh * C_GROUP + h) * CHD + t] = f2bf(__fdividef(oo, dd));
+    a.out[((size_t)b * a.nq + kvh * C_GROUP + h) * CHD + t] = f2bf(dd > 0.f ? __fdividef(oo, dd) : 0.f);
   }
 }
 

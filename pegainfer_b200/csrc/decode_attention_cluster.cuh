@@ -28,5 +28,8 @@ struct ClusterAttnArgs {
   PfSpan pf[kMaxPfSpans];
 };
 cudaError_t launch_decode_attention_cluster(const ClusterAttnArgs& a, int nkv, int bs, cudaStream_t stream);
+// round-2 kernel (decode_attention_tma.cu): TMA page tiles + mma.sync, up to 16-CTA clusters.  Same argument block
+// (prefetch spans ignored).  Returns a cudaError, or -2 when it cannot take the call.
+int launch_decode_attention_tma(const ClusterAttnArgs& a, int nkv, int bs, cudaStream_t stream);
 
 }  // namespace pk

@@ -7,7 +7,6 @@
 //   * CTA states merged into the leader CTA over distributed shared memory, no global synchronisation
 // q arrives normed + roped (qk_norm_partial_rope_batched_decode_hd256_cuda), the step's K/V row is already in the
 // pool: nothing is requested before griddepcontrol.wait.  fp32 throughout, one bf16 rounding of O / d.
-// STATUS: written without GPU time left; parity test is opt-in (tests/test_qwen35_ops_gpu.py, PK_TEST_QWEN35=1).
 #include "common.cuh"
 
 namespace pk {
@@ -50,6 +49,10 @@ __device__ __forceinline__ uint32_t h2_map_to_rank(const void* smem_ptr, uint32_
 __device__ __forceinline__ void h2_st_cluster(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// split cluster barrier: arrive at kernel entry, wait right before the first remote shared-memory store, so every
+// CTA of the cluster is known to have started (its shared memory exists) before anyone writes into it
+__device__ __forceinline__ void h2_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void h2_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void h2_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -81,6 +84,7 @@ decode_attention_hd256_kernel(const Hd256Args a) {
   const bf16* kbase = a.kv + a.k_off + (int64_t)kvh * H2 + lane * 8;
   const bf16* vbase = a.kv + a.v_off + (int64_t)kvh * H2 + lane * 8;
 
+  h2_cluster_arrive();  // opening barrier (completed by h2_cluster_wait before the DSMEM stores)
   pdl_launch_dependents();
   pdl_wait();
 
@@ -189,6 +193,7 @@ decode_attention_hd256_kernel(const Hd256Args a) {
     dst[1] = make_float4(o[h][4], o[h][5], o[h][6], o[h][7]);
   }
   __syncthreads();
+  h2_cluster_wait();
   const int t = threadIdx.x;  // 256 threads = 256 output dims
 #pragma unroll
   for (int h = 0; h < H2_GROUP; ++h) {
@@ -223,7 +228,7 @@ decode_attention_hd256_kernel(const Hd256Args a) {
       dd = fmaf(c_d[r][h], wt, dd);
       oo = fmaf(c_o[r][h][t], wt, oo);
     }
-    a.out[((size_t)b * a.nq + kvh * H2_GROUP + h) * H2 + t] = f2bf(__fdividef(oo, dd));
+    a.out[((size_t)b * a.nq + kvh * H2_GROUP + h) * H2 + t] = f2bf(dd > 0.f ? __fdividef(oo, dd) : 0.f);  // len == 0 -> zeros
   }
 }
 

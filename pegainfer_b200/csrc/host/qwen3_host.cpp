@@ -139,6 +139,8 @@ static const int kPrefillCtaTileQ = 64;  // config.rs:5
 static const int kRopePositions = 4096;  // weights.rs:300
 static const int kPageSize = 16;         // weights.rs:309
 
+static int bucket_for(int bs);
+
 struct Qwen3Model {
   KernelLib k;
   DeviceContext ctx;
@@ -296,18 +298,30 @@ bool Qwen3Model::load_tensor(const std::string& name, const void* data, int rows
   tp.shard_range(c.num_key_value_heads * c.head_dim, &kv_off, &kv_rows);
   tp.shard_range(c.intermediate_size, &i_off, &i_rows);
   bool ok = true;
+  // full-shape check for every tensor (weight_loader.rs:130-206 asserts shapes; a mismatched checkpoint must fail
+  // with the tensor name instead of reading out of bounds)
+  auto want = [&](int er, int ec) -> bool {
+    if (rows == er && cols == ec) return true;
+    char b[200];
+    snprintf(b, sizeof b, "%s: shape [%d, %d] does not match the expected [%d, %d]", name.c_str(), rows, cols, er, ec);
+    fail(b);
+    return false;
+  };
+  const int Q = c.num_attention_heads * c.head_dim, KV = c.num_key_value_heads * c.head_dim;
   if (name == "model.embed_tokens.weight") {
-    if (rows != c.vocab_size || cols != H) return fail("embed_tokens shape mismatch");
+    if (!want(c.vocab_size, H)) return false;
     ok = alloc_matrix(embed_tokens, rows, cols) && upload_rows(embed_tokens, 0, data, cols, 0, rows);
   } else if (name == "lm_head.weight") {
     if (c.tie_word_embeddings) return true;  // tied: weights.rs:104-107
-    if (rows != c.vocab_size || cols != H) return fail("lm_head shape mismatch");
+    if (!want(c.vocab_size, H)) return false;
     has_lm_head = true;
     ok = alloc_matrix(lm_head, rows, cols) && upload_rows(lm_head, 0, data, cols, 0, rows);
   } else if (name == "model.norm.weight") {
+    if (!want(1, H)) return false;
     ok = upload_vec(norm, data, H);
   } else if (name.rfind("model.layers.", 0) == 0) {
     const size_t dot = name.find('.', 13);
+    if (dot == std::string::npos) return fail("unknown tensor " + name);
     const int li = atoi(name.substr(13, dot - 13).c_str());
     if (li < 0 || li >= c.num_hidden_layers) return fail("layer index out of range: " + name);
     TransformerBlock& L = layers[li];
@@ -315,31 +329,32 @@ bool Qwen3Model::load_tensor(const std::string& name, const void* data, int rows
     Attention& A = L.attention;
     A.q_dim = q_rows;
     A.kv_dim = kv_rows;
-    if (sub == "input_layernorm.weight") ok = upload_vec(L.input_layernorm, data, H);
-    else if (sub == "post_attention_layernorm.weight") ok = upload_vec(L.post_attention_layernorm, data, H);
-    else if (sub == "self_attn.q_norm.weight") ok = upload_vec(A.q_norm, data, c.head_dim);
-    else if (sub == "self_attn.k_norm.weight") ok = upload_vec(A.k_norm, data, c.head_dim);
+    if (sub == "input_layernorm.weight") ok = want(1, H) && upload_vec(L.input_layernorm, data, H);
+    else if (sub == "post_attention_layernorm.weight") ok = want(1, H) && upload_vec(L.post_attention_layernorm, data, H);
+    else if (sub == "self_attn.q_norm.weight") ok = want(1, c.head_dim) && upload_vec(A.q_norm, data, c.head_dim);
+    else if (sub == "self_attn.k_norm.weight") ok = want(1, c.head_dim) && upload_vec(A.k_norm, data, c.head_dim);
     else if (sub == "self_attn.q_proj.weight" || sub == "self_attn.k_proj.weight" ||
              sub == "self_attn.v_proj.weight") {
       // DeviceMatrix::vstack([q, k, v]) (weights.rs:182): written straight into the fused matrix
-      if (cols != H) return fail(name + ": cols != hidden_size");
+      if (!want(sub[10] == 'q' ? Q : KV, H)) return false;
       ok = alloc_matrix(A.qkv_proj, (size_t)q_rows + 2 * kv_rows, H);
       if (sub[10] == 'q') ok = ok && upload_rows(A.qkv_proj, 0, data, cols, q_off, q_rows);
       else if (sub[10] == 'k') ok = ok && upload_rows(A.qkv_proj, q_rows, data, cols, kv_off, kv_rows);
       else ok = ok && upload_rows(A.qkv_proj, (size_t)q_rows + kv_rows, data, cols, kv_off, kv_rows);
     } else if (sub == "self_attn.o_proj.weight") {  // column shard (weight_loader.rs:168-206)
-      if (rows != H) return fail(name + ": rows != hidden_size");
+      if (!want(H, Q)) return false;
       ok = alloc_matrix(A.o_proj, H, q_rows) && upload_cols(A.o_proj, data, rows, cols, q_off, q_rows);
     } else if (sub == "mlp.gate_proj.weight" || sub == "mlp.up_proj.weight") {
-      if (cols != H) return fail(name + ": cols != hidden_size");
+      if (!want(c.intermediate_size, H)) return false;
       ok = alloc_matrix(L.mlp.gate_up_proj, (size_t)2 * i_rows, H);
       ok = ok && upload_rows(L.mlp.gate_up_proj, sub[4] == 'g' ? 0 : i_rows, data, cols, i_off, i_rows);
     } else if (sub == "mlp.down_proj.weight") {
-      if (rows != H) return fail(name + ": rows != hidden_size");
+      if (!want(H, c.intermediate_size)) return false;
       ok = alloc_matrix(L.mlp.down_proj, H, i_rows) && upload_cols(L.mlp.down_proj, data, rows, cols, i_off, i_rows);
     } else {
       return fail("unknown tensor " + name);
     }
+    if (!ok && !err.empty() && err.find("does not match") != std::string::npos) return false;
   } else {
     return fail("unknown tensor " + name);
   }
@@ -390,7 +405,6 @@ bool Qwen3Model::finalize() {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     num_pages = (int)std::max<size_t>(64, (size_t)((double)free_b * 0.85) / ((size_t)layout.page_stride * 2));
-    num_pages = std::min(num_pages, 16384);
   }
   if (!kv_buffer.alloc_zeros((size_t)num_pages * layout.page_stride * 2)) return fail("KvPool alloc failed");
   pool.init(num_pages);
@@ -405,12 +419,15 @@ bool Qwen3Model::finalize() {
 bool Qwen3Model::create_decode_buffers() {
   const Config& c = config;
   max_bs = std::max(1, std::min(rt.max_batch, 64));
+  // graph buckets pad the batch up to {1,2,4,...,64} (batch_decode_buffers.rs:12): the buffers must hold the bucket
+  if (rt.enable_cuda_graph && bucket_for(max_bs) > 0) max_bs = bucket_for(max_bs);
   const int bs = max_bs, H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim();
   bool ok = normed.zeros(H, bs) && q.zeros(qd, bs) && kbuf.zeros(kd, bs) && v.zeros(kd, bs) &&
             attn_out.zeros(qd, bs) && attn_proj.zeros(H, bs) && gate_up_out.zeros(2 * local_inter(), bs) &&
             mlp_act.zeros(local_inter(), bs) && mlp_out.zeros(H, bs) && hidden.zeros(H, bs) &&
             hidden_b.zeros(H, bs) && logits.zeros(c.vocab_size, bs) && zero_residual.alloc_zeros((size_t)H * bs * 2);
-  max_total_pages = std::min(pool.capacity, 8192);
+  // a request never holds more than 4096 / 16 pages (RoPE table bound), so this covers any legal batch
+  max_total_pages = max_bs * (kRopePositions / kPageSize);
   const int slots = bs * kSplitMaxChunks;
   int o = 0;
   mo.token_ids = o; o += bs;
@@ -477,19 +494,51 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   const Config& c = config;
   const int H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim(), I = local_inter();
   const int nh = local_heads(), nkv = local_kv_heads(), hd = c.head_dim;
+  // ---- plan, then commit (the reference validates the whole batch before any KvState changes): every check that
+  // can reject the call runs first; seq_len / pages are only touched once nothing below can fail for a
+  // data-dependent reason, and a CUDA failure later rolls them back (PrefillTxn). ----
   int T = 0;
   std::vector<int> starts(n_req);
+  if (n_req <= 0) return fail("empty prefill batch");
+  if (n_req > max_bs) return fail("more prompts than max_batch");
+  int pages_needed = 0;
   for (int i = 0; i < n_req; ++i) {
     if (kv_ids[i] < 0 || kv_ids[i] >= (int)kv_states.size() || !kv_states[kv_ids[i]].live)
       return fail("bad kv id");
+    for (int j = 0; j < i; ++j)
+      if (kv_ids[j] == kv_ids[i]) return fail("duplicate kv id in one prefill batch");
     if (lens[i] <= 0) return fail("empty prompt");
-    starts[i] = kv_states[kv_ids[i]].seq_len;
+    const KvState& s = kv_states[kv_ids[i]];
+    starts[i] = s.seq_len;
+    if (starts[i] + lens[i] > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
+    pages_needed += std::max(0, (starts[i] + lens[i] + kPageSize - 1) / kPageSize - (int)s.pages.size());
     T += lens[i];
   }
+  if (pages_needed > (int)pool.free_list.size()) {
+    char b[128];
+    snprintf(b, sizeof b, "KvState: out of pages (need %d more, %d available)", pages_needed,
+             (int)pool.free_list.size());
+    return fail(b);
+  }
+  struct PrefillTxn {  // undo record: restores seq_len and returns the pages acquired by this call
+    Qwen3Model* m;
+    std::vector<std::pair<int, std::pair<int, size_t>>> old;  // kv id -> (seq_len, page count)
+    bool committed = false;
+    ~PrefillTxn() {
+      if (committed) return;
+      for (auto& o : old) {
+        KvState& s = m->kv_states[o.first];
+        std::vector<int> extra(s.pages.begin() + o.second.second, s.pages.end());
+        m->pool.release(extra);
+        s.pages.resize(o.second.second);
+        s.seq_len = o.second.first;
+      }
+    }
+  } txn{this, {}, false};
   for (int i = 0; i < n_req; ++i) {
     KvState& s = kv_states[kv_ids[i]];
-    if (starts[i] + lens[i] > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
-    if (!ensure_capacity(s, starts[i] + lens[i])) return false;
+    txn.old.push_back({kv_ids[i], {s.seq_len, s.pages.size()}});
+    if (!ensure_capacity(s, starts[i] + lens[i])) return false;  // cannot fail: counted above
     s.seq_len += lens[i];
   }
   // ---- PrefillPagedPlan::new_batch_with_cta_tile_q (ops/attention.rs:208-302) ----
@@ -544,15 +593,17 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
       return hs.data.alloc_uninit(dim * cap * 2);
     };
     if (!(grow(pf_hid, H) && grow(pf_hid_out, H) && grow(pf_nrm, H) && grow(pf_q, qd) && grow(pf_k, kd) &&
-          grow(pf_v, kd) && grow(pf_o, H) && grow(pf_gu, 2 * I) && grow(pf_act, I) && grow(pf_att, qd) &&
-          pf_plan.alloc_uninit((size_t)cap * 16 + (size_t)max_total_pages * 4 + 65536)))
+          grow(pf_v, kd) && grow(pf_o, H) && grow(pf_gu, 2 * I) && grow(pf_act, I) && grow(pf_att, qd)))
       return fail("prefill buffer allocation failed");
     prefill_capacity = cap;
+  }
+  if (plan_pack.size() * 4 > pf_plan.bytes) {
+    cudaStreamSynchronize(ctx.stream);
+    if (!pf_plan.alloc_uninit(plan_pack.size() * 4 + 65536)) return fail("prefill plan buffer allocation failed");
   }
   HiddenStates &hid = pf_hid, &hid_out = pf_hid_out, &nrm = pf_nrm, &qb = pf_q, &kb = pf_k, &vb = pf_v, &ob = pf_o,
                &gu = pf_gu, &act = pf_act, &att = pf_att;
   cudaStream_t st = ctx.stream;
-  if (plan_pack.size() * 4 > pf_plan.bytes) return fail("prefill plan larger than its buffer");
   if (!cu(cudaMemcpyAsync(pf_plan.ptr, plan_pack.data(), plan_pack.size() * 4, cudaMemcpyHostToDevice, st), "plan H2D"))
     return false;
   const int* P = pf_plan.i32();
@@ -611,13 +662,14 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   for (int i = 0; i < n_req; ++i) {
     const int last = off + lens[i] - 1;
     pk_bf16* lg = logits.data.bf() + (size_t)i * c.vocab_size;
-    if (i >= max_bs) return fail("more prompts than max_batch");
     k.rms_norm_cuda(hcur + (size_t)last * H, norm.data.bf(), normed.data.bf() + (size_t)i * H, H, eps, st);
     k.gemm_graphsafe_cuda(output_projection().data.bf(), normed.data.bf() + (size_t)i * H, lg, c.vocab_size, 1, H, st);
     logits_out[i] = lg;
     off += lens[i];
   }
-  return cu(cudaStreamSynchronize(st), "prefill sync");  // buffers above are freed on return
+  if (!cu(cudaStreamSynchronize(st), "prefill sync")) return false;
+  txn.committed = true;
+  return true;
 }
 
 // ===================================================================== decode (batch_decode.rs)
@@ -857,12 +909,29 @@ bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, con
                                  bool* split_out) {
   const bool fused = rt.mode >= 1;
   std::vector<int> positions(bs);
+  // validate the whole step first, then commit (no request is advanced unless every request can be)
+  int pages_needed = 0, table_pages = 0;
   for (int b = 0; b < bs; ++b) {
     if (kv_ids[b] < 0 || kv_ids[b] >= (int)kv_states.size() || !kv_states[kv_ids[b]].live) return fail("bad kv id");
+    for (int j = 0; j < b; ++j)
+      if (kv_ids[j] == kv_ids[b]) return fail("duplicate kv id in one decode batch");
+    const KvState& s = kv_states[kv_ids[b]];
+    if (s.seq_len + 1 > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
+    const int need = (s.seq_len + 1 + kPageSize - 1) / kPageSize;
+    pages_needed += std::max(0, need - (int)s.pages.size());
+    table_pages += std::max(need, (int)s.pages.size());
+  }
+  if (pages_needed > (int)pool.free_list.size()) {
+    char eb[128];
+    snprintf(eb, sizeof eb, "KvState: out of pages (need %d more, %d available)", pages_needed,
+             (int)pool.free_list.size());
+    return fail(eb);
+  }
+  if (table_pages + (padded - bs) > max_total_pages + max_bs) return fail("page table overflow");
+  for (int b = 0; b < bs; ++b) {
     KvState& s = kv_states[kv_ids[b]];
     positions[b] = s.seq_len;
-    if (s.seq_len + 1 > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
-    if (!ensure_capacity(s, s.seq_len + 1)) return false;
+    if (!ensure_capacity(s, s.seq_len + 1)) return false;  // cannot fail: counted above
     s.seq_len += 1;
   }
   memset(mh, 0, meta_bytes);
@@ -872,7 +941,6 @@ bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, con
   for (int b = 0; b < padded; ++b) {
     if (b < bs) {
       const KvState& s = kv_states[kv_ids[b]];
-      if (np + (int)s.pages.size() > max_total_pages + max_bs) return fail("page table overflow");
       memcpy(mh + mo.page_indices + np, s.pages.data(), s.pages.size() * 4);
       np += (int)s.pages.size();
       mh[mo.last_page_len + b] = s.last_page_len(kPageSize);
@@ -978,6 +1046,13 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
 bool Qwen3Model::decode_burst(int kv_id, uint32_t first_token, int K, uint32_t* tokens_out, float* ms_total) {
   if (!finalized || rt.mode < 1) return fail("decode_burst needs the fused path");
   if (K <= 0) return fail("K must be positive");
+  {  // all K steps must fit before the first one advances the request
+    if (kv_id < 0 || kv_id >= (int)kv_states.size() || !kv_states[kv_id].live) return fail("bad kv id");
+    const KvState& s = kv_states[kv_id];
+    if (s.seq_len + K > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
+    const int need = (s.seq_len + K + kPageSize - 1) / kPageSize - (int)s.pages.size();
+    if (need > (int)pool.free_list.size()) return fail("KvState: out of pages for the burst");
+  }
   DeviceBuf staged;
   if (!staged.alloc_zeros((size_t)K * meta_bytes)) return fail("burst staging alloc failed");
   std::vector<int> host((size_t)K * mo.total_ints);

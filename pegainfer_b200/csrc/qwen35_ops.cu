@@ -324,7 +324,8 @@ void rms_norm_gated_cuda(const pk_bf16* x, const float* weight, const pk_bf16* g
 }
 void conv1d_prefill_cuda(const pk_bf16* x_seq, const pk_bf16* conv_weight, pk_bf16* conv_state, pk_bf16* out_seq, int num_channels,
                          int seq_len, int kernel_size, pk_stream stream) {
-  if (num_channels <= 0 || seq_len <= 0 || kernel_size < 1 || kernel_size > 9) return;
+  if (num_channels <= 0 || seq_len <= 0) return;
+  if (kernel_size < 1 || kernel_size > 9) unsupported("conv1d_prefill_cuda", "kernel_size must be 1..9");
   const int64_t total = (int64_t)num_channels * seq_len;
   launch(conv1d_silu_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, true, (const bf16*)x_seq,
          (const bf16*)conv_weight, (const bf16*)conv_state, (bf16*)out_seq, num_channels, seq_len, kernel_size);
@@ -334,7 +335,9 @@ void conv1d_prefill_cuda(const pk_bf16* x_seq, const pk_bf16* conv_weight, pk_bf
 void gated_delta_rule_decode_cuda(const pk_bf16* qkv, const pk_bf16* b_proj, const pk_bf16* a_proj, const pk_bf16* dt_bias,
                                   const float* A_log, float* state, pk_bf16* output, int num_key_heads, int num_value_heads,
                                   int key_dim, int val_dim, pk_stream stream) {
-  if (key_dim != GK || val_dim != GV || num_value_heads <= 0 || num_key_heads <= 0) return;  // the reference's fixed 128 x 128 heads
+  if (num_value_heads <= 0 || num_key_heads <= 0) return;
+  if (key_dim != GK || val_dim != GV)  // the reference's fixed 128 x 128 heads (gated_delta_rule.cu asserts the same)
+    unsupported("gated_delta_rule_decode_cuda", "key_dim and val_dim must be 128");
   launch(gated_delta_rule_decode_kernel, dim3(num_value_heads), dim3(GV * GS), 0, stream, true, (const bf16*)qkv, (const bf16*)b_proj,
          (const bf16*)a_proj, (const bf16*)dt_bias, A_log, state, (bf16*)output, num_key_heads, num_value_heads);
 }
@@ -352,7 +355,8 @@ void prefill_attention_hd256_prep_cuda(const pk_bf16* q_full_batch, const pk_bf1
                                        const pk_bf16* sin_cache, pk_bf16* q_batch_out, pk_bf16* k_cache, pk_bf16* v_cache,
                                        int num_q_heads, int num_kv_heads, int seq_len, const int* start_pos_ptr, int rotary_dim,
                                        float rms_eps, int max_seq_len, pk_stream stream) {
-  if (seq_len <= 0 || rotary_dim % 16 != 0 || rotary_dim > HD2) return;
+  if (seq_len <= 0) return;
+  if (rotary_dim % 16 != 0 || rotary_dim > HD2) unsupported("prefill_attention_hd256_prep_cuda", "rotary_dim must be a multiple of 16, <= 256");
   const int64_t items = (int64_t)seq_len * (num_q_heads + 2 * num_kv_heads);
   launch(hd256_prefill_prep_kernel, dim3((unsigned)((items + 7) / 8)), dim3(256), 0, stream, true, (const bf16*)q_full_batch,
          (const bf16*)k_batch, (const bf16*)v_batch, (const bf16*)q_norm_weight, (const bf16*)k_norm_weight, (const bf16*)cos_cache,
@@ -363,7 +367,9 @@ void qk_norm_partial_rope_batched_decode_hd256_cuda(const pk_bf16* q_full_batch,
                                                     const pk_bf16* k_norm_weight, const pk_bf16* cos_cache, const pk_bf16* sin_cache,
                                                     const int* positions, pk_bf16* q_batch_out, int num_q_heads, int num_kv_heads,
                                                     int batch_size, int rotary_dim, float rms_eps, pk_stream stream) {
-  if (batch_size <= 0 || rotary_dim % 16 != 0 || rotary_dim > HD2) return;
+  if (batch_size <= 0) return;
+  if (rotary_dim % 16 != 0 || rotary_dim > HD2)
+    unsupported("qk_norm_partial_rope_batched_decode_hd256_cuda", "rotary_dim must be a multiple of 16, <= 256");
   const int items = batch_size * (num_q_heads + num_kv_heads);
   launch(hd256_decode_prep_kernel, dim3((items + 7) / 8), dim3(256), 0, stream, true, (const bf16*)q_full_batch, (bf16*)k_batch,
          (const bf16*)q_norm_weight, (const bf16*)k_norm_weight, (const bf16*)cos_cache, (const bf16*)sin_cache, positions,

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const bf16* __re
   }
   total = block_reduce_sum_f(total, sm);
   const float u = (float)(splitmix64(seed) >> 40) * (1.0f / 16777216.0f) * total;
-  if (tid == 0) s_pick = -1;
+  if (tid == 0) s_pick = 0x7fffffff;
+  __syncthreads();
   float running = 0.f;
   int last_ok = -1;
   for (int base = 0; base < n; base += kSampleThreads) {
@@ -263,10 +264,12 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const bf16* __re
       __syncthreads();
     }
     const float incl = running + s_scan[tid];
-    if (pv > 0.f && incl > u && incl - pv <= u) atomicMax(&s_pick, -1), atomicCAS(&s_pick, -1, i);
+    // first eligible index whose inclusive prefix exceeds u: prefixes are non-decreasing in i, so the minimum
+    // over all candidates of the first block that has one is the inverse-CDF pick (deterministic)
+    if (pv > 0.f && incl > u) atomicMin(&s_pick, i);
     running += s_scan[kSampleThreads - 1];
     __syncthreads();
-    if (s_pick >= 0) break;
+    if (s_pick != 0x7fffffff) break;
   }
   // rounding at the very end of the CDF: fall back to the last eligible token
   int lo_all = last_ok;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const bf16* __re
   if ((tid & 31) == 0) s_last[tid >> 5] = lo_all;
   __syncthreads();
   if (tid == 0) {
-    int pick = s_pick;
+    int pick = s_pick == 0x7fffffff ? -1 : s_pick;
     if (pick < 0) {
       for (int w = 0; w < kSampleThreads / 32; ++w) pick = max(pick, s_last[w]);
       if (pick < 0) pick = 0;

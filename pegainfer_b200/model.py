@@ -98,7 +98,8 @@ class Qwen3Model:
     def __init__(self, cfg: Qwen3Config, weights,
                  runtime: ModelRuntimeConfig | None = None, tp_comm: int | None = None):
         """``weights``: dict or iterable of (HF tensor name, bf16 tensor on host or device); every
-        tensor is the FULL unsharded matrix, the loader takes this rank's shard (weights.rs:121-291)."""
+        tensor is the FULL unsharded matrix, the loader takes this rank's shard (weights.rs:121-291).
+        ``None``: stream tensors in with ``load_tensor`` and call ``finalize()``."""
         rt = runtime or ModelRuntimeConfig()
         rt.tensor_parallel.validate_for(cfg)
         if not torch.cuda.is_available():
@@ -116,15 +117,26 @@ class Qwen3Model:
         self._m = self._h.pq_model_create(C.byref(pc), C.byref(pr), lib_path.encode(), tp_comm)
         if not self._m:
             raise RuntimeError("pq_model_create: " + self._h.pq_create_error().decode())
-        for name, t in (weights.items() if isinstance(weights, dict) else weights):
-            if name == "lm_head.weight" and cfg.tie_word_embeddings:
-                continue
-            if t.is_cuda:
-                torch.cuda.current_stream().synchronize()
-            assert t.dtype == torch.bfloat16 and t.is_contiguous(), name
-            rows, cols = (t.shape[0], t.shape[1]) if t.dim() == 2 else (1, t.shape[0])
-            self._ck(self._h.pq_model_load_tensor(self._m, name.encode(), t.data_ptr(), rows, cols))
+        self._finalized = False
+        if weights is not None:
+            for name, t in (weights.items() if isinstance(weights, dict) else weights):
+                self.load_tensor(name, t)
+            self.finalize()
+
+    def load_tensor(self, name: str, t: torch.Tensor) -> None:
+        """Feed one FULL (unsharded) HF tensor; the loader keeps this rank's shard.  For callers that stream a
+        checkpoint into several models at once (``weights=None`` at construction, then ``finalize()``)."""
+        if name == "lm_head.weight" and self.cfg.tie_word_embeddings:
+            return
+        if t.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        assert t.dtype == torch.bfloat16 and t.is_contiguous(), name
+        rows, cols = (t.shape[0], t.shape[1]) if t.dim() == 2 else (1, t.shape[0])
+        self._ck(self._h.pq_model_load_tensor(self._m, name.encode(), t.data_ptr(), rows, cols))
+
+    def finalize(self) -> None:
         self._ck(self._h.pq_model_finalize(self._m))
+        self._finalized = True
 
     @classmethod
     def from_safetensors(cls, model_path: str, runtime: ModelRuntimeConfig | None = None, tp_comm: int | None = None):
