@@ -483,7 +483,7 @@ static int attention_impl() {
 }
 static bool use_cluster_attention() { return attention_impl() >= 1; }
 static int launch_cluster_or_tma(const ClusterAttnArgs& c, int nkv, int bs, cudaStream_t stream) {
-  if (attention_impl() == 2 && c.npf == 0) {
+  if (attention_impl() == 2) {  // (the L2-prefetch spans are an experiment of the round-1 cluster kernel only)
     const int rc = launch_decode_attention_tma(c, nkv, bs, stream);
     if (rc != -2) return rc;
   }

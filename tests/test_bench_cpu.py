@@ -12,11 +12,24 @@ from pegainfer_b200.synthetic import random_weights, to_numpy_bits
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cpu_decode_rate_outlives_one_page_pool():
+def test_cpu_decode_rate_at_the_gpu_arms_context():
+    """The CPU arm decodes at the GPU arm's context length (pre-filled KV, no CPU prefill), with the OpenMP team size
+    set explicitly and read back, three timed repeats."""
     cfg = PRESETS["qwen3-tiny"]
     w = to_numpy_bits(random_weights(cfg, seed=0, device="cpu"))
-    rate, n, dt = bench.cpu_decode_rate(cfg, w, 300, budget_s=30.0)  # 300 steps >> the old fixed 8-page pool
-    assert n == 300 and rate > 0 and dt > 0
+    rate, runs, n, threads, ctx_end = bench.cpu_decode_rate(cfg, w, 2048, budget_s=3.0)
+    assert rate > 0 and len(runs) == 3 and n >= 2 and threads >= 1
+    assert ctx_end == 2048 + 2 + 3 * n  # warm-up step + calibration step + the timed steps, all past the filled context
+
+
+def test_oracle_thread_control_and_row_spreading():
+    import numpy as np
+    from oracle import qwen3_oracle as O
+    assert O.set_num_threads(2) == 2 and O.get_max_threads() == 2
+    O.set_num_threads(os.cpu_count() or 1)
+    a = np.arange(7 * 33, dtype=np.uint16).reshape(7, 33)
+    b = O.spread_rows(a)
+    assert b is not a and (a == b).all()
 
 
 def test_reference_arm_prints_contract_line():
@@ -28,3 +41,5 @@ def test_reference_arm_prints_contract_line():
                 "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] >= 1 and len(line["cpu_baseline"]["runs"]) == 3
+    assert "OpenMP" in line["cpu_baseline"]["sample"] and "ctx" in line["cpu_baseline"]["sample"]

@@ -283,7 +283,8 @@ def test_paged_kv_scatter(lib, nkv):
 
 
 @pytest.mark.parametrize("seq_lens,nq,nkv", [([1], 32, 8), ([128], 32, 8), ([191, 33, 1], 32, 8), ([700], 4, 1),
-                                             ([1500, 900], 32, 8)])
+                                             ([1500, 900], 32, 8), ([4090], 32, 8), ([3000, 17, 640], 32, 8),
+                                             ([100, 260, 16, 15, 17], 32, 8), ([4096], 8, 2), ([300, 3000], 16, 4)])
 def test_paged_attention_decode(lib, seq_lens, nq, nkv):
     hd, layer, bs = 128, 1, len(seq_lens)
     pg = Paged(seq_lens, nkv, seed=3)
@@ -519,7 +520,7 @@ def test_gemv_fused_prologue_epilogue(N):
 
 
 # ------------------------------------------------------------------ fused decode attention (+ L2 prefetch clusters)
-@pytest.mark.parametrize("seq_lens", [[1], [300], [2300, 77]])
+@pytest.mark.parametrize("seq_lens", [[1], [300], [2300, 77], [4095], [17, 2049, 512, 16]])
 def test_decode_attention_fused_matches_unfused_ops(seq_lens):
     """pk_b200_decode_attention_fused == qk_norm_rope_batched_decode + paged_kv_scatter + paged_attention_decode
     (oracle composition, batch_decode.rs:196-247), and the prefetch variant returns the same bits."""

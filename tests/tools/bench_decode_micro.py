@@ -7,6 +7,12 @@ Attention: the reference's own case (1 layer, nq 32, nkv 8, hd 128, page 16, bs 
 4096*seq + 16 KiB, seq in {1, 128, 1024, 4096}.  When oracle/_ref/libkernels_ref.so is present the reference's own
 kernels (cuBLAS GEMV, FlashInfer decode) are timed beside ours under the same protocol.
 
+Round 2 adds the `train` protocol next to the single-launch one (single CUDA-event launches quantise to ~2 us and
+cannot resolve the small shapes): N >= 32 launches over N DISTINCT cold buffers (together >= 2 x L2, after an L2
+sweep), captured into ONE CUDA graph so no host launch gap sits between them, one event pair around the replay;
+per-launch time = total / N.  For our library it is reported with programmatic dependent launch off and on (on = what
+the decode graph runs: the next launch's weight / KV requests overlap this one's tail).
+
 Prints one JSON object; `python tests/tools/bench_decode_micro.py > gpurun_out/micro.json`.
 """
 import json
@@ -43,6 +49,39 @@ def cold_time(fn, iters=ITERS):
     return ts[len(ts) // 2], ts[0]
 
 
+def train_time(launch, n, reps=5):
+    """`launch(i, stream)` enqueues the kernel on buffer copy i.  n launches in one CUDA graph, cold L2 before each
+    replay; returns (median, min) microseconds PER LAUNCH."""
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    for i in range(n):
+        launch(i, st)  # warm-up outside capture (lazy attribute setup, tensor maps)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=side):
+        for i in range(n):
+            launch(i, side.cuda_stream)
+    ts = []
+    for _ in range(reps):
+        flush_sink.copy_(flush.view(torch.int64).sum())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / n)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def copies_for(nbytes):
+    return int(max(32, min(64, math.ceil((256 << 20) / max(nbytes, 1))))) if nbytes < (64 << 20) else (4 if nbytes < (1 << 29) else 2)
+
+
+def stat(by, med, best, peak, digits=3):
+    return {"us": round(med, 2), "us_min": round(best, 2), "gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, digits)}
+
+
 def load_libs():
     libs = {"b200": ffi.lib()}
     ref = os.path.join(ROOT, "oracle", "_ref", "libkernels_ref.so")
@@ -72,9 +111,21 @@ def bench_gemv(libs, peak):
         row = {"shape": name, "M": M, "K": K, "bytes": by}
         for tag, lib in libs.items():
             med, best = cold_time(lambda: lib.gemm_cuda(W.data_ptr(), X.data_ptr(), Y.data_ptr(), M, 1, K, st))
-            row[tag] = {"us": round(med, 2), "us_min": round(best, 2), "gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, 3)}
+            row[tag] = stat(by, med, best, peak)
+        nc = copies_for(by)
+        Ws = [W] + [W.clone() for _ in range(nc - 1)]
+        row["train_launches"] = max(32, nc)
+        for tag, lib in libs.items():
+            for pdl in ((0, 1) if tag == "b200" else (0,)):
+                if tag == "b200":
+                    lib.pk_b200_set_pdl(pdl)
+                med, best = train_time(lambda i, s_: lib.gemm_graphsafe_cuda(Ws[i % nc].data_ptr(), X.data_ptr(), Y.data_ptr(), M, 1, K, s_),
+                                       max(32, nc))
+                row[tag + (".train_pdl" if pdl else ".train")] = stat(by, med, best, peak)
+            if tag == "b200":
+                lib.pk_b200_set_pdl(0)
         rows.append(row)
-        del W
+        del W, Ws
     return rows
 
 
@@ -101,16 +152,21 @@ def bench_attention(libs, peak):
         oip, csz_d, full = i32([0, n]), i32([csz]), i32([seq])
         tmp_v = torch.zeros((64, nq * hd), dtype=torch.bfloat16, device="cuda")
         tmp_s = torch.zeros((64, nq), dtype=torch.float32, device="cuda")
+        nc = copies_for(by)
+        kvs = [kv] + [kv.clone() for _ in range(nc - 1)]
+        row["train_launches"] = nc
         for tag, lib in libs.items():
             if seq < 1024:
-                fn = lambda: lib.paged_attention_decode_cuda(q.data_ptr(), out.data_ptr(), kv.data_ptr(), 0, ps * nkv * hd, pi.data_ptr(),
-                    ip.data_ptr(), lpl.data_ptr(), req.data_ptr(), tile.data_ptr(), full.data_ptr(), nq, nkv, hd, ps, 1, stride, sm, st)
+                fn = lambda i=0, s_=st: lib.paged_attention_decode_cuda(q.data_ptr(), out.data_ptr(), kvs[i % nc].data_ptr(), 0, ps * nkv * hd, pi.data_ptr(),
+                    ip.data_ptr(), lpl.data_ptr(), req.data_ptr(), tile.data_ptr(), full.data_ptr(), nq, nkv, hd, ps, 1, stride, sm, s_)
             else:
-                fn = lambda: lib.paged_attention_decode_split_kv_cuda(q.data_ptr(), out.data_ptr(), kv.data_ptr(), 0, ps * nkv * hd,
+                fn = lambda i=0, s_=st: lib.paged_attention_decode_split_kv_cuda(q.data_ptr(), out.data_ptr(), kvs[i % nc].data_ptr(), 0, ps * nkv * hd,
                     pi.data_ptr(), ip.data_ptr(), lpl.data_ptr(), req.data_ptr(), tile.data_ptr(), csz_d.data_ptr(), oip.data_ptr(),
-                    mask.data_ptr(), tmp_v.data_ptr(), tmp_s.data_ptr(), nq, nkv, hd, ps, 1, 64, stride, sm, st)
+                    mask.data_ptr(), tmp_v.data_ptr(), tmp_s.data_ptr(), nq, nkv, hd, ps, 1, 64, stride, sm, s_)
             med, best = cold_time(fn)
-            row[tag + ".abi"] = {"us": round(med, 2), "us_min": round(best, 2), "gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, 4)}
+            row[tag + ".abi"] = stat(by, med, best, peak, 4)
+            med, best = train_time(fn, nc)
+            row[tag + ".abi.train"] = stat(by, med, best, peak, 4)
         # the fused B200 entry (QK-norm + RoPE + KV append + attention + merge in one launch)
         k1, v1 = pattern(nkv * hd, 0.001), pattern(nkv * hd, 0.001)
         qn, kn = torch.ones(hd, device="cuda", dtype=torch.bfloat16), torch.ones(hd, device="cuda", dtype=torch.bfloat16)
@@ -119,11 +175,17 @@ def bench_attention(libs, peak):
         max_chunks = min(64, (2 * torch.cuda.get_device_properties(0).multi_processor_count + nkv - 1) // nkv)  # as the host sizes it
         partial = torch.zeros(64 * nq * (hd + 2) * 2, device="cuda", dtype=torch.float32)
         counters = torch.zeros(64, device="cuda", dtype=torch.int32)
-        fn = lambda: b200.pk_b200_decode_attention_fused(q.data_ptr(), k1.data_ptr(), v1.data_ptr(), out.data_ptr(), kv.data_ptr(), 0,
+        fn = lambda i=0, s_=st: b200.pk_b200_decode_attention_fused(q.data_ptr(), k1.data_ptr(), v1.data_ptr(), out.data_ptr(), kvs[i % nc].data_ptr(), 0,
             ps * nkv * hd, pi.data_ptr(), ip.data_ptr(), lpl.data_ptr(), pos.data_ptr(), qn.data_ptr(), kn.data_ptr(), cos.data_ptr(),
-            sin.data_ptr(), 1e-6, partial.data_ptr(), counters.data_ptr(), 64, max_chunks, nq, nkv, hd, ps, 1, stride, sm, st)
+            sin.data_ptr(), 1e-6, partial.data_ptr(), counters.data_ptr(), 64, max_chunks, nq, nkv, hd, ps, 1, stride, sm, s_)
         med, best = cold_time(fn)
-        row["b200.fused"] = {"us": round(med, 2), "us_min": round(best, 2), "gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, 4)}
+        row["b200.fused"] = stat(by, med, best, peak, 4)
+        for pdl in (0, 1):
+            b200.pk_b200_set_pdl(pdl)
+            med, best = train_time(fn, nc)
+            row["b200.fused.train_pdl" if pdl else "b200.fused.train"] = stat(by, med, best, peak, 4)
+        b200.pk_b200_set_pdl(0)
+        del kvs
         rows.append(row)
     return rows
 
@@ -135,7 +197,7 @@ def main():
     except Exception:
         pass
     libs = load_libs()
-    res = {"protocol": f"cold L2 (512 MiB read sweep before each launch), median of {ITERS} single launches, CUDA events", "hbm_peak_gbs": peak,
+    res = {"protocol": f"single: cold L2 (512 MiB read sweep before each launch), median of {ITERS} single launches, CUDA events; train: >= 32 launches over distinct cold buffers in one CUDA graph, per-launch = total / N, median of 5 replays", "hbm_peak_gbs": peak,
            "gemv": bench_gemv(libs, peak), "decode_attention": bench_attention(libs, peak)}
     print(json.dumps(res, indent=1))
 
