@@ -55,11 +55,12 @@ PARITY_TOL_ULP = 8
 
 
 # ------------------------------------------------------------------------------------ helpers
-def weight_bytes_per_token(cfg, world=1):
-    """SURVEY.md 8d / BASELINE.md 2: decode weight bytes per token per GPU."""
+def weight_bytes_per_token(cfg, world=1, lm_head_rows=None):
+    """SURVEY.md 8d / BASELINE.md 2: decode weight bytes per token per GPU (`lm_head_rows`: the rows of the output
+    projection this rank streams -- the whole vocabulary unless lm_head is vocab-sharded)."""
     H, I, L, V = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size
     per_layer = 2 * (H * (cfg.q_dim + 2 * cfg.kv_dim) + H * cfg.q_dim + 3 * H * I)
-    return L * per_layer // world + 2 * V * H
+    return L * per_layer // world + 2 * (V if lm_head_rows is None else lm_head_rows) * H
 
 
 def kv_bytes_per_ctx_token(cfg, world=1):
@@ -271,10 +272,10 @@ def parity_check(model, cfg, prompt_len, world, rank, dist):
         return {"checked": False, "why": f"no fixture {os.path.basename(path)}"} if rank == 0 else None
     fx = F.Fixture(path)
     kv = model.alloc_kv()
-    rows = [model.prefill([synthetic_prompt(prompt_len)], [kv])[0]]
+    rows = [model.gather_logits(model.prefill([synthetic_prompt(prompt_len)], [kv]), dist)[0]]
     for t in fx.tokens:
         lg, _ = model.decode([t], [kv])
-        rows.append(lg[0])
+        rows.append(model.gather_logits(lg, dist)[0])
     model.drop_request(kv)
     if rank != 0:
         return None
@@ -408,7 +409,8 @@ def run_ours(args, cfg, rank, world, dist):
 
     # ---- roofline of the dominant kernel (decode GEMV), live CUDA-event timing ----
     peak, peak_src = measured_peaks()
-    wbytes = weight_bytes_per_token(cfg, world)
+    lm_rows = model.logits_shard()[0]
+    wbytes = weight_bytes_per_token(cfg, world, lm_rows)
     roof = None
     if world == 1:
         ms_pass, n_gemv = model.bench_gemv_pass(20)
@@ -455,6 +457,8 @@ def run_ours(args, cfg, rank, world, dist):
                 "config": {"workload": bench_workload_name(cfg, world), "prompt_len": prompt_len,
                            "decode_ctx": [ctx_lo, ctx_lo + K], "l2": "inputs (weights 8-15 GB/token) >> 126 MB L2, no flush needed",
                            "parallelism": f"tp{world}", "cuda_graph": True, "pdl": True,
+                           "lm_head": "vocab-sharded (max/index exchange)" if lm_rows != cfg.vocab_size else "full",
+                           "tp_collective": (os.environ.get("PK_TP_MODE", "ll") + " (GEMV-fused LL all-reduce over NVLink peer memory)") if world > 1 else None,
                            "checkpoint": "random-init N(0, 0.02), seed 0, generated on the CPU (the oracle fixtures' checkpoint)",
                            "decode_impl": "persistent single-launch step" if persistent else "fused multi-kernel graph",
                            "launches_per_step": launches_per_step, "model_load_s": round(load_s, 1)},

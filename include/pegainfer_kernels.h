@@ -201,7 +201,16 @@ int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16* const* Y,
  *             publishes the sequence flag (release.sys); Y is not written.
  *   x_mode 2: like x_mode 1, but `residual` is the all-reduce result: after all ranks' flags are seen the
  *             prologue sums the `world` partials from local staging in rank order (fp32, one bf16 rounding),
- *             adds the residual stream X and applies RMSNorm.  Pairs with the previous epi-2 launch. */
+ *             adds the residual stream X and applies RMSNorm.  Pairs with the previous epi-2 launch.
+ *   epi 3:    GEMV and its all-reduce in ONE kernel, row tile by row tile (the default for TP decode): every CTA
+ *             rounds its partial rows to bf16, stores them as 8-byte {2 x bf16, seq} lines straight into every
+ *             peer's staging area over NVLink (flag travels with the data: no fence, no flag store, no ticket),
+ *             then polls ITS OWN rows' lines from the peers in local memory, sums in rank order (fp32, one bf16
+ *             rounding -- bit-identical on every rank, and to the standalone collective) and writes the REDUCED
+ *             rows to Y[0].  All ranks launch the same grid, so CTA c owns the same rows everywhere.  seq =
+ *             (*tp_step) * 256 + tp_op + 1: `tp_step` is a device word the host advances once per decode step on
+ *             every rank (part of the step's metadata block), `tp_op` the op's index inside the step (baked into
+ *             the CUDA graph); the staging slot alternates with tp_op's parity. */
 typedef struct {
   const pk_bf16* W;
   const pk_bf16* X;
@@ -215,7 +224,9 @@ typedef struct {
   pk_bf16* hidden_out;
   pk_bf16* normed_out;
   int epi;
-  void* tp_comm; /* pk_tp_comm*, required for x_mode 2 / epi 2 (tensor parallel) */
+  void* tp_comm; /* pk_tp_comm*, required for x_mode 2 / epi 2 / epi 3 (tensor parallel) */
+  const uint32_t* tp_step; /* epi 3: device word, the decode step counter (same value on every rank) */
+  int tp_op;               /* epi 3: index of this collective inside the step (0..254) */
 } pk_b200_gemv_args;
 int pk_b200_gemv_fused(const pk_b200_gemv_args* args, pk_stream stream);
 /* Ring depth (2..12 stages of 8 row segments), CTAs per SM and K elements per row segment (multiple of
@@ -369,6 +380,12 @@ pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
 void pk_tp_comm_destroy(pk_tp_comm* comm);
 /* Largest row count one call can reduce for rows of hidden_dim bf16 (callers chunk above it). */
 int64_t pk_tp_max_rows(pk_tp_comm* comm, int hidden_dim);
+/* Vocab-sharded lm_head: combine every rank's (max logit, index inside its shard) into the global greedy token on
+ * every rank (highest value, lowest global index on ties).  `index_inout[b]`: local index in, global winner out.
+ * `step_counter` != NULL (CUDA-graph path): sequence = (*step_counter) * 256 + seq_or_op + 1; NULL: `seq_or_op` is
+ * the absolute sequence number chosen by the host (must differ from call to call and be identical on all ranks). */
+int pk_tp_top1_exchange(pk_tp_comm* comm, const pk_bf16* local_max, int* index_inout, int batch_size, int vocab_offset,
+                        const uint32_t* step_counter, uint32_t seq_or_op, pk_stream stream);
 /* all_reduce_hidden(&mut HiddenStates): in-place SUM (fp32 in rank order, one bf16 rounding). */
 int pk_tp_all_reduce(pk_tp_comm* comm, pk_bf16* hidden, int64_t n, pk_stream stream);
 int pk_tp_all_reduce_rows(pk_tp_comm* comm, pk_bf16* hidden, int hidden_dim, int rows,

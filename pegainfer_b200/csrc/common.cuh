@@ -173,11 +173,21 @@ struct TpDev {
   uint32_t* flags[kTpMaxWorld];  // flags[p]: rank p's flag array  [2][kTpMaxCtas][world] + ctl
   int rank, world;
   int64_t slot_bytes;            // bytes per (slot, src) region
-  int64_t raw_bytes;             // leading part of a region used for plain rows; the tail is the LL area
+  int64_t raw_bytes;             // leading part of a region used for plain rows; the tail holds the two LL areas
+  int64_t ll_off, ll_bytes;      // LL lines of the standalone all-reduce kernel (PK_TP_PROTO=ll)
+  int64_t gll_off, gll_bytes;    // 8-byte LL lines of the GEMV-fused all-reduce (gemv.cu epi 3)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile_v2(void* p, uint32_t x, uint32_t y) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;

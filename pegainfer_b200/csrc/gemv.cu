@@ -38,8 +38,11 @@ struct GemvArgs {
   float eps;
   bf16* hidden_out;
   bf16* normed_out;
-  int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows), 2 push partial rows to all TP peers
-  TpDev tp;     // x_mode 2 / epi 2: peer staging + flags
+  int epi;      // 0 plain, 1 SwiGLU (W has 2*M rows: gate rows then up rows), 2 push partial rows to all TP peers,
+                // 3 all-reduce of this CTA's rows inside the kernel (8-byte LL lines over NVLink)
+  TpDev tp;     // x_mode 2 / epi 2 / epi 3: peer staging + flags
+  const uint32_t* tp_step;  // epi 3: decode step counter (device word, identical on every rank)
+  int tp_op;                // epi 3: collective index inside the step
   int stages;
   int kc;       // K elements per row segment per stage (multiple of 256); stage = 8 segments
 };
@@ -282,7 +285,7 @@ gemv_stream_kernel(const GemvArgs a) {
     for (int n = 0; n < NTOK; ++n) acc[n] = (acc4[n][0] + acc4[n][1]) + (acc4[n][2] + acc4[n][3]);
 #pragma unroll
     for (int n = 0; n < NTOK; ++n) acc[n] = warp_sum(acc[n]);
-    if (a.epi == 2) {
+    if (a.epi >= 2) {
       if (has_row && lane == 0) {
 #pragma unroll
         for (int n = 0; n < NTOK; ++n) ybuf[n * 64 + (out_row - r0)] = acc[n];
@@ -311,6 +314,58 @@ gemv_stream_kernel(const GemvArgs a) {
           a.Y[0][(size_t)n * M + out_row] = f2bf(gt / (1.0f + expf(-gt)) * up);
         }
       }
+    }
+  }
+  if (a.epi == 3) {
+    // ---- GEMV + all-reduce in one kernel, row tile by row tile.  Every rank runs the same grid, so CTA c owns rows
+    // [r0, r1) on every rank: push my bf16 partials of these rows to the peers as 8-byte {2 x bf16, seq} lines (the
+    // sequence number travels with the data: one posted NVLink store per line, no fence / flag / ticket), then poll
+    // the peers' lines for the SAME rows in local memory and sum in rank order (fp32, one bf16 rounding: the
+    // collective's bf16 result, bit-identical on every rank). ----
+    consumer_bar();
+    const int me = a.tp.rank, W = a.tp.world;
+    const uint32_t seq = (*a.tp_step) * 256u + (uint32_t)a.tp_op + 1u;  // read after griddepcontrol.wait
+    const int slot = a.tp_op & 1;
+    const int nrows = r1 - r0;
+    constexpr int NP = (NTOK + 1) / 2;  // token pairs per row
+    const int items = nrows * NP;
+    auto payload = [&](int it) -> uint32_t {
+      const int r = it % nrows, pr = it / nrows;
+      const float v0 = ybuf[(2 * pr) * 64 + r];
+      const float v1 = (2 * pr + 1 < NTOK) ? ybuf[(2 * pr + 1) * 64 + r] : 0.f;
+      return pack_bf16(v0, v1);
+    };
+    for (int idx = threadIdx.x; idx < items * (W - 1); idx += kConsumerThreads) {
+      const int pi = idx / items, it = idx - pi * items;
+      const int p = pi >= me ? pi + 1 : pi;
+      const int r = it % nrows, pr = it / nrows;
+      uint8_t* line = a.tp.stage[p] + (size_t)(slot * W + me) * a.tp.slot_bytes + a.tp.gll_off +
+                      ((size_t)pr * M + r0 + r) * 8;
+      st_volatile_v2(line, payload(it), seq);
+    }
+    const uint8_t* local = a.tp.stage[me] + (size_t)slot * W * a.tp.slot_bytes + a.tp.gll_off;
+    for (int it = threadIdx.x; it < items; it += kConsumerThreads) {
+      const int r = it % nrows, pr = it / nrows;
+      float s0 = 0.f, s1 = 0.f;
+      for (int q = 0; q < W; ++q) {
+        uint32_t v;
+        if (q == me) {
+          v = payload(it);
+        } else {
+          const uint8_t* line = local + (size_t)q * a.tp.slot_bytes + ((size_t)pr * M + r0 + r) * 8;
+          uint2 l;
+          uint32_t spins = 0;
+          do {
+            l = ld_volatile_v2(line);
+            if (++spins > (1u << 24)) __trap();  // a missing peer becomes a launch failure, not a hang
+          } while (l.y != seq);
+          v = l.x;
+        }
+        s0 += bf16_lo(v);
+        s1 += bf16_hi(v);
+      }
+      a.Y[0][(size_t)(2 * pr) * M + r0 + r] = f2bf(s0);
+      if (2 * pr + 1 < NTOK) a.Y[0][(size_t)(2 * pr + 1) * M + r0 + r] = f2bf(s1);
     }
   }
   if (a.epi == 2) {
@@ -427,7 +482,7 @@ static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
     configured[NTOK] = smem;
   }
   const int grid = gemv_grid(a.M, a.epi);
-  if (a.epi == 2 && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
+  if (a.epi >= 2 && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
   return launch(kern, dim3(grid), dim3(kConsumerThreads + 32), smem, stream, true, a);
 }
 
@@ -519,6 +574,14 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
     if (!comm) return -1;
     if ((int64_t)g->N * (g->epi == 2 ? g->M : g->K) * 2 > comm->d.raw_bytes) return -2;
     a.tp = comm->d;
+  }
+  if (g->epi == 3) {
+    const pk_tp_comm* comm = static_cast<const pk_tp_comm*>(g->tp_comm);
+    if (!comm || !g->tp_step || g->tp_op < 0 || g->tp_op > 254) return -1;
+    if ((int64_t)((g->N + 1) / 2) * g->M * 8 > comm->d.gll_bytes - 4096) return -2;  // the last 4 KB hold the top-1 lines
+    a.tp = comm->d;
+    a.tp_step = g->tp_step;
+    a.tp_op = g->tp_op;
   }
   return (int)launch_gemv(a, g->N, stream);
 }

@@ -34,7 +34,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused) PQ_OPT(pk_b200_gemm_segments)
   PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
-  PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid)
+  PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid) PQ_OPT(pk_tp_top1_exchange)
 #undef PQ_REQ
 #undef PQ_OPT
   if (!missing.empty()) return "kernel library " + p + " lacks:" + missing;
@@ -176,7 +176,7 @@ struct Qwen3Model {
   struct MetaOff {
     int token_ids, positions, page_indptr, last_page_len, request_indices, kv_tile_indices,
         kv_chunk_size, split_request, split_tile, split_chunk, split_o_indptr, page_indices,
-        split_mask_bytes, total_ints;
+        split_mask_bytes, step_seq, total_ints;
   } mo{};
   DeviceBuf split_tmp_v, split_tmp_s;
   DeviceBuf attn_partial, attn_counters;
@@ -185,13 +185,31 @@ struct Qwen3Model {
   int* sample_h = nullptr;
   std::map<int, std::unique_ptr<CudaGraphState>> graphs;
   int max_seq_len_step = 0, split_padded_slots = 0;
+  uint32_t step_counter = 0;  // decode steps issued so far: the sequence base of the GEMV-fused all-reduces (every rank
+                              // issues the same steps in the same order, so the counters agree across ranks)
 
   int local_heads() const { return config.num_attention_heads / tp.world_size; }
   int local_kv_heads() const { return config.num_key_value_heads / tp.world_size; }
   int local_inter() const { return config.intermediate_size / tp.world_size; }
   int local_q_dim() const { return local_heads() * config.head_dim; }
   int local_kv_dim() const { return local_kv_heads() * config.head_dim; }
-  const DeviceMatrix& output_projection() const { return has_lm_head ? lm_head : embed_tokens; }
+  // Vocab-sharded lm_head: on the fused TP path every rank streams only rows [rank * V/N, (rank+1) * V/N)
+  // of the output projection and the greedy token is agreed on with a (max, index) exchange; the reference keeps
+  // lm_head replicated (weights.rs:104-119), which is what mode 0 (its op sequence) still does.
+  bool vocab_sharded() const {
+    return tp.is_sharded() && rt.mode >= 1 && tp_comm && k.pk_tp_top1_exchange && config.vocab_size % tp.world_size == 0 &&
+           (config.vocab_size / tp.world_size) % 8 == 0;
+  }
+  int local_vocab() const { return vocab_sharded() ? config.vocab_size / tp.world_size : config.vocab_size; }
+  int vocab_offset() const { return vocab_sharded() ? tp.rank * (config.vocab_size / tp.world_size) : 0; }
+  const DeviceMatrix& output_projection_full() const { return has_lm_head ? lm_head : embed_tokens; }
+  // this rank's rows of the output projection: the whole matrix, or its vocabulary shard
+  const pk_bf16* output_rows() const {
+    const DeviceMatrix& m = output_projection_full();
+    return (vocab_sharded() && !lm_head_is_shard) ? m.data.bf() + (size_t)vocab_offset() * m.cols : m.data.bf();
+  }
+  bool lm_head_is_shard = false;  // untied lm_head uploaded as the local shard only
+  uint32_t host_sample_seq = 0;
 
   bool fail(const std::string& m) {
     err = m;
@@ -315,7 +333,12 @@ bool Qwen3Model::load_tensor(const std::string& name, const void* data, int rows
     if (c.tie_word_embeddings) return true;  // tied: weights.rs:104-107
     if (!want(c.vocab_size, H)) return false;
     has_lm_head = true;
-    ok = alloc_matrix(lm_head, rows, cols) && upload_rows(lm_head, 0, data, cols, 0, rows);
+    if (vocab_sharded()) {  // keep only this rank's vocabulary rows
+      lm_head_is_shard = true;
+      ok = alloc_matrix(lm_head, local_vocab(), cols) && upload_rows(lm_head, 0, data, cols, vocab_offset(), local_vocab());
+    } else {
+      ok = alloc_matrix(lm_head, rows, cols) && upload_rows(lm_head, 0, data, cols, 0, rows);
+    }
   } else if (name == "model.norm.weight") {
     if (!want(1, H)) return false;
     ok = upload_vec(norm, data, H);
@@ -425,7 +448,7 @@ bool Qwen3Model::create_decode_buffers() {
   bool ok = normed.zeros(H, bs) && q.zeros(qd, bs) && kbuf.zeros(kd, bs) && v.zeros(kd, bs) &&
             attn_out.zeros(qd, bs) && attn_proj.zeros(H, bs) && gate_up_out.zeros(2 * local_inter(), bs) &&
             mlp_act.zeros(local_inter(), bs) && mlp_out.zeros(H, bs) && hidden.zeros(H, bs) &&
-            hidden_b.zeros(H, bs) && logits.zeros(c.vocab_size, bs) && zero_residual.alloc_zeros((size_t)H * bs * 2);
+            hidden_b.zeros(H, bs) && logits.zeros(local_vocab(), bs) && zero_residual.alloc_zeros((size_t)H * bs * 2);
   // a request never holds more than 4096 / 16 pages (RoPE table bound), so this covers any legal batch
   max_total_pages = max_bs * (kRopePositions / kPageSize);
   const int slots = bs * kSplitMaxChunks;
@@ -440,6 +463,7 @@ bool Qwen3Model::create_decode_buffers() {
   mo.split_request = o; o += slots;
   mo.split_tile = o; o += slots;
   mo.split_chunk = o; o += 1;
+  mo.step_seq = o; o += 1;
   mo.split_o_indptr = o; o += bs + 1;
   mo.split_mask_bytes = o; o += (slots + 3) / 4;
   mo.page_indices = o; o += max_total_pages + bs;
@@ -661,9 +685,9 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   int off = 0;
   for (int i = 0; i < n_req; ++i) {
     const int last = off + lens[i] - 1;
-    pk_bf16* lg = logits.data.bf() + (size_t)i * c.vocab_size;
+    pk_bf16* lg = logits.data.bf() + (size_t)i * local_vocab();
     k.rms_norm_cuda(hcur + (size_t)last * H, norm.data.bf(), normed.data.bf() + (size_t)i * H, H, eps, st);
-    k.gemm_graphsafe_cuda(output_projection().data.bf(), normed.data.bf() + (size_t)i * H, lg, c.vocab_size, 1, H, st);
+    k.gemm_graphsafe_cuda(output_rows(), normed.data.bf() + (size_t)i * H, lg, local_vocab(), 1, H, st);
     logits_out[i] = lg;
     off += lens[i];
   }
@@ -727,7 +751,7 @@ bool Qwen3Model::decode_kernels_compat(int bs, bool split) {
     const DeviceVec& nw = li + 1 < c.num_hidden_layers ? layers[li + 1].input_layernorm : norm;
     k.fused_add_rms_norm_batched_cuda(hidden.data.bf(), mlp_out.data.bf(), nw.data.bf(), normed.data.bf(), H, bs, eps, st);
   }
-  gemm_decode(output_projection(), 0, c.vocab_size, normed.data.bf(), bs, logits.data.bf());
+  k.gemm_graphsafe_cuda(output_rows(), normed.data.bf(), logits.data.bf(), local_vocab(), bs, H, ctx.stream);
   return true;
 }
 
@@ -745,6 +769,7 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
   pk_bf16* Ha = hidden.data.bf();
   pk_bf16* Hb = hidden_b.data.bf();
   k.embedding_batched_cuda(embed_tokens.data.bf(), reinterpret_cast<const uint32_t*>(M + mo.token_ids), Ha, H, bs, st);
+  int tp_op = 0;
   auto gemv = [&](const pk_bf16* W, const pk_bf16* X, int Mrows, int K, pk_bf16* y0, pk_bf16* y1, pk_bf16* y2,
                   int s0, int s1, int s2, int x_mode, const pk_bf16* residual, const pk_bf16* nw, pk_bf16* hout,
                   int epi) -> bool {
@@ -756,6 +781,10 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
     g.x_mode = x_mode; g.residual = residual; g.norm_w = nw; g.eps = eps;
     g.hidden_out = hout; g.normed_out = nullptr; g.epi = epi;
     g.tp_comm = tp_comm;
+    if (epi == 3) {  // all-reduce inside the GEMV: sequence = (step counter, op index)
+      g.tp_step = reinterpret_cast<const uint32_t*>(M + mo.step_seq);
+      g.tp_op = tp_op++;
+    }
     if (k.pk_b200_gemv_fused(&g, st) != 0) return fail("pk_b200_gemv_fused rejected its arguments");
     return true;
   };
@@ -796,21 +825,29 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
       return fail("pk_b200_decode_attention_fused_prefetch failed");
     return true;
   };
-  // Tensor parallel, two variants (both custom kernels over NVLink peer memory, no NCCL on the data path):
-  //  * kernel (default): one-shot all-reduce kernel fused with add + RMSNorm between the GEMVs (7 launches/layer).
-  //  * fused (PK_TP_FUSED=1): the row-parallel GEMVs (o_proj, down_proj) push their partial rows to every rank
+  // Tensor parallel, three variants (all custom kernels over NVLink peer memory, no NCCL on the data path; PK_TP_MODE):
+  //  * kernel: one-shot all-reduce kernel fused with add + RMSNorm between the GEMVs (7 launches/layer).
+  //  * fused: the row-parallel GEMVs (o_proj, down_proj) push their partial rows to every rank
   //    (epi 2) and the following GEMV's prologue reduces them (x_mode 2): 5 launches per layer, the layer's two
   //    all-reduces live inside the GEMVs.
   //  Measured (Qwen3-8B, bs 1, profiles/README.md): 2 x B200 398 vs 367 tok/s, 8 x B200 411 vs 350 tok/s -- every one
   //  of the push epilogue's ~300 CTAs pays a system-scope fence after its remote stores and the grid ticket
-  //  serialises behind them, which costs more than a single-CTA collective launch.  Kept as an opt-in experiment.
-  static const int tp_fused_env = [] {
-    const char* e = getenv("PK_TP_FUSED");
-    return e ? atoi(e) : -1;
+  //  serialises behind them, which costs more than a single-CTA collective launch.
+  //  * ll (default): the row-parallel GEMVs reduce their own rows INSIDE the kernel (epi 3: 8-byte {data, seq} lines
+  //    pushed to the peers, each CTA polls and sums its own rows) and write the reduced vector; the following GEMV
+  //    takes the plain residual prologue of the single-GPU path.  5 launches per layer, no fence, no flag, no ticket.
+  static const int tp_mode_env = [] {  // 0 kernel, 1 fused (flag protocol), 2 ll
+    const char* e = getenv("PK_TP_MODE");
+    if (e && strcmp(e, "kernel") == 0) return 0;
+    if (e && strcmp(e, "fused") == 0) return 1;
+    const char* f = getenv("PK_TP_FUSED");  // round-1 switch
+    if (f && !e) return atoi(f) > 0 ? 1 : 0;
+    return 2;
   }();
-  const bool tp_fuse = tp_on && tp_fused_env > 0;
-  const int red_mode = tp_on ? 2 : 1;
-  const int push_epi = tp_on ? 2 : 0;
+  const bool tp_ll = tp_on && tp_mode_env == 2;
+  const bool tp_fuse = tp_on && tp_mode_env >= 1;
+  const int red_mode = (tp_on && !tp_ll) ? 2 : 1;
+  const int push_epi = tp_on ? (tp_ll ? 3 : 2) : 0;
   const pk_bf16* prev_residual = zero_residual.bf();  // layer 0: hidden + 0
   if (tp_on && !tp_fuse) {
     k.rms_norm_batched_cuda(Ha, layers[0].input_layernorm.data.bf(), normed.data.bf(), H, bs, eps, st);
@@ -838,8 +875,8 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
                                           st) != 0)
         return fail("pk_tp_all_reduce_add_rms_norm failed");
     }
-    if (!gemv(output_projection().data.bf(), normed.data.bf(), c.vocab_size, H, logits.data.bf(), nullptr, nullptr,
-              c.vocab_size, 0, 0, 0, nullptr, nullptr, nullptr, 0))
+    if (!gemv(output_rows(), normed.data.bf(), local_vocab(), H, logits.data.bf(), nullptr, nullptr,
+              local_vocab(), 0, 0, 0, nullptr, nullptr, nullptr, 0))
       return false;
   } else {
     for (int li = 0; li < c.num_hidden_layers; ++li) {
@@ -862,15 +899,19 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
         return false;
       prev_residual = mlp_out.data.bf();
     }
-    if (!gemv(output_projection().data.bf(), Ha, c.vocab_size, H, logits.data.bf(), nullptr, nullptr, c.vocab_size, 0,
+    if (!gemv(output_rows(), Ha, local_vocab(), H, logits.data.bf(), nullptr, nullptr, local_vocab(), 0,
               0, red_mode, prev_residual, norm.data.bf(), Hb, 0))
       return false;
   }
   // greedy token for every request inside the same graph
   for (int b = 0; b < bs; ++b)
-    k.flashinfer_top1_cuda(logits.data.bf() + (size_t)b * c.vocab_size, static_cast<pk_bf16*>(top1_val.ptr) + b,
+    k.flashinfer_top1_cuda(logits.data.bf() + (size_t)b * local_vocab(), static_cast<pk_bf16*>(top1_val.ptr) + b,
                            static_cast<uint8_t*>(top1_states.ptr) + (size_t)b * 8192, sample_out.i32() + b,
-                           c.vocab_size, st);
+                           local_vocab(), st);
+  if (vocab_sharded() &&
+      k.pk_tp_top1_exchange(tp_comm, static_cast<pk_bf16*>(top1_val.ptr), sample_out.i32(), bs, vocab_offset(),
+                            reinterpret_cast<const uint32_t*>(M + mo.step_seq), 250u, st) != 0)
+    return fail("pk_tp_top1_exchange failed");
   return true;
 }
 
@@ -885,7 +926,7 @@ bool Qwen3Model::decode_kernels_persistent() {
   g.vocab_size = c.vocab_size; g.num_q_heads = local_heads(); g.num_kv_heads = local_kv_heads();
   g.head_dim = c.head_dim; g.page_size = kPageSize;
   g.rms_eps = c.rms_norm_eps; g.sm_scale = 1.0f / sqrtf((float)c.head_dim);
-  g.embed = embed_tokens.data.bf(); g.lm_head = output_projection().data.bf(); g.final_norm = norm.data.bf();
+  g.embed = embed_tokens.data.bf(); g.lm_head = output_projection_full().data.bf(); g.final_norm = norm.data.bf();
   g.cos_cache = cos_cache.data.bf(); g.sin_cache = sin_cache.data.bf(); g.zero_residual = zero_residual.bf();
   g.token_ids = reinterpret_cast<const uint32_t*>(M + mo.token_ids);
   g.positions = M + mo.positions; g.page_indices = M + mo.page_indices; g.page_indptr = M + mo.page_indptr;
@@ -935,6 +976,7 @@ bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, con
     s.seq_len += 1;
   }
   memset(mh, 0, meta_bytes);
+  mh[mo.step_seq] = (int)(++step_counter & 0xffffffu);
   int np = 0;
   max_seq_len_step = 0;
   mh[mo.page_indptr] = 0;
@@ -1034,7 +1076,7 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
       for (int b = 0; b < bs; ++b) sampled[b] = sample_h[b];
     } else {
       for (int b = 0; b < bs; ++b)  // per request: top-1 kernel, sync, 4-byte D2H (sampling.rs:161-172)
-        if (!sample_greedy(logits.data.bf() + (size_t)b * config.vocab_size, sampled + b)) return false;
+        if (!sample_greedy(logits.data.bf() + (size_t)b * local_vocab(), sampled + b)) return false;
     }
   }
   return true;
@@ -1120,7 +1162,7 @@ bool Qwen3Model::bench_gemv_pass(int iters, float* ms_per_pass, int* launches_pe
            gemv(L.mlp.down_proj.data.bf(), mlp_act.data.bf(), H, I, mlp_out.data.bf(), 0, nullptr, nullptr, nullptr, 0);
       n += 4;
     }
-    ok = ok && gemv(output_projection().data.bf(), hidden.data.bf(), c.vocab_size, H, logits.data.bf(), 1,
+    ok = ok && gemv(output_projection_full().data.bf(), hidden.data.bf(), c.vocab_size, H, logits.data.bf(), 1,
                     zero_residual.bf(), norm.data.bf(), hidden_b.data.bf(), 0);
     n += 1;
     return ok;
@@ -1146,7 +1188,11 @@ bool Qwen3Model::bench_gemv_pass(int iters, float* ms_per_pass, int* launches_pe
 
 bool Qwen3Model::sample_greedy(const pk_bf16* lg, int* out) {
   k.flashinfer_top1_cuda(lg, static_cast<pk_bf16*>(top1_val.ptr), static_cast<uint8_t*>(top1_states.ptr),
-                         sample_out.i32(), config.vocab_size, ctx.stream);
+                         sample_out.i32(), local_vocab(), ctx.stream);
+  if (vocab_sharded() &&  // `lg` is this rank's vocabulary shard: agree on the global winner (every rank makes this call)
+      k.pk_tp_top1_exchange(tp_comm, static_cast<pk_bf16*>(top1_val.ptr), sample_out.i32(), 1, vocab_offset(), nullptr,
+                            0x80000000u | (++host_sample_seq & 0x7fffffffu), ctx.stream) != 0)
+    return fail("pk_tp_top1_exchange failed");
   if (!cu(cudaMemcpyAsync(sample_h, sample_out.ptr, 4, cudaMemcpyDeviceToHost, ctx.stream), "sample D2H")) return false;
   if (!cu(cudaStreamSynchronize(ctx.stream), "sample sync")) return false;
   *out = sample_h[0];
@@ -1291,6 +1337,11 @@ __attribute__((visibility("default"))) int pq_bench_gemv_pass(void* mp, int iter
   return PQ_M->bench_gemv_pass(iters, ms_per_pass, n) ? 0 : -1;
 }
 __attribute__((visibility("default"))) int64_t pq_launches_per_step(void* mp) { return PQ_M->launches_per_step; }
+// width of the logits rows this rank returns: vocab_size, or its vocabulary shard on the fused TP path (offset in *off)
+__attribute__((visibility("default"))) int pq_logits_cols(void* mp, int* off) {
+  if (off) *off = PQ_M->vocab_offset();
+  return PQ_M->local_vocab();
+}
 __attribute__((visibility("default"))) int64_t pq_meta_bytes(void* mp) { return (int64_t)PQ_M->meta_bytes; }
 // record a CUDA event pair around caller-driven work on the model's stream (bench.py e2e leg)
 __attribute__((visibility("default"))) void* pq_event_record(void* mp) {

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
         if (p == me) continue;
         uint8_t* region = a.d.stage[p] + (size_t)(slot * W + me) * a.d.slot_bytes;
         if (LL) {
-          uint8_t* line = region + a.d.raw_bytes + ((size_t)t * nv + i) * 32;
+          uint8_t* line = region + a.d.ll_off + ((size_t)t * nv + i) * 32;
           st_volatile_v4(line, v.x, seq, v.y, seq);
           st_volatile_v4(line + 16, v.z, seq, v.w, seq);
         } else {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
         if (r == me) {
           v = reinterpret_cast<const uint4*>(a.partial + (size_t)t * a.dim)[i];
         } else if (LL) {
-          const uint8_t* line = local + (size_t)r * a.d.slot_bytes + a.d.raw_bytes + ((size_t)t * nv + i) * 32;
+          const uint8_t* line = local + (size_t)r * a.d.slot_bytes + a.d.ll_off + ((size_t)t * nv + i) * 32;
           uint4 l0, l1;
           do { l0 = ld_volatile_v4(line); } while (l0.y != seq || l0.w != seq);
           do { l1 = ld_volatile_v4(line + 16); } while (l1.y != seq || l1.w != seq);
@@ -164,6 +164,56 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
   }
 }
 
+// Vocab-sharded lm_head under tensor parallelism: every rank holds the (max logit, GLOBAL index) of its vocabulary
+// shard; one 16-byte {value, index, seq, seq} line per request is pushed to every peer (posted NVLink stores, the
+// sequence travels with the data) and every rank picks the same winner: highest value, lowest index on ties (the
+// single-GPU top-1 rule).  Replaces a replicated lm_head GEMV (1.24 GB per token per rank for Qwen3-8B).
+struct TpTop1Args {
+  TpDev d;
+  const bf16* vals;   // [bs] local maxima
+  int* idx;           // [bs] in: local index inside the shard, out: global winner
+  int bs, vocab_offset, entry0;
+  const uint32_t* step;  // device step counter (graph path) or null
+  uint32_t seq_arg;      // op index (with `step`) or the absolute sequence number
+};
+
+__global__ void __launch_bounds__(64) tp_top1_exchange_kernel(const TpTop1Args a) {
+  pdl_wait();
+  const int t = threadIdx.x;
+  if (t >= a.bs) return;
+  const int me = a.d.rank, W = a.d.world;
+  const uint32_t seq = a.step ? (*a.step) * 256u + a.seq_arg + 1u : a.seq_arg;
+  const float v = bf2f(a.vals[t]);
+  const int gi = a.idx[t] + a.vocab_offset;
+  const int64_t off = a.d.gll_off + a.d.gll_bytes - 4096 + (int64_t)(a.entry0 + t) * 16;
+  for (int p = 0; p < W; ++p)
+    if (p != me) {
+      uint8_t* line = a.d.stage[p] + (size_t)me * a.d.slot_bytes + off;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(__float_as_uint(v)), "r"((uint32_t)gi),
+                   "r"(seq), "r"(seq)
+                   : "memory");
+    }
+  float bv = v;
+  int bi = gi;
+  for (int q = 0; q < W; ++q) {
+    if (q == me) continue;
+    const uint8_t* line = a.d.stage[me] + (size_t)q * a.d.slot_bytes + off;
+    uint4 l;
+    uint32_t spins = 0;
+    do {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "l"(line) : "memory");
+      if (++spins > (1u << 24)) __trap();
+    } while (l.z != seq || l.w != seq);
+    const float ov = __uint_as_float(l.x);
+    const int oi = (int)l.y;
+    if (ov > bv || (ov == bv && oi < bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  a.idx[t] = bi;
+}
+
 }  // namespace pk
 
 
@@ -193,8 +243,13 @@ pk_tp_comm* pk_tp_comm_create(int rank, int world, void* const* staging_ptrs,
   }
   c->staging_bytes = staging_bytes;
   c->d.slot_bytes = (staging_bytes / (2 * world)) & ~(int64_t)15;
-  // plain rows use the whole region unless the LL protocol is on, which reserves the last quarter for its lines
-  c->d.raw_bytes = tp_use_ll() ? ((c->d.slot_bytes - c->d.slot_bytes / 4) & ~(int64_t)15) : c->d.slot_bytes;
+  // region = [plain rows: 3/4][LL lines of the standalone kernel: 1/8][LL lines of the GEMV-fused all-reduce: 1/8]
+  const int64_t eighth = (c->d.slot_bytes / 8) & ~(int64_t)15;
+  c->d.raw_bytes = c->d.slot_bytes - 2 * eighth;
+  c->d.ll_off = c->d.raw_bytes;
+  c->d.ll_bytes = eighth;
+  c->d.gll_off = c->d.raw_bytes + eighth;
+  c->d.gll_bytes = eighth;
   return c;
 }
 
@@ -217,7 +272,7 @@ static int tp_launch(pk_tp_comm* comm, const pk_bf16* partial, pk_bf16* hidden,
   const int grid = T < kTpMaxCtas ? T : kTpMaxCtas;
   const size_t smem = mode == 1 ? sizeof(float) * ((size_t)dim + 40) : sizeof(float) * 40;
   // LL lines need 4 bytes per element; messages that do not fit the LL area use the flag protocol
-  const bool ll = tp_use_ll() && (int64_t)T * dim * 4 <= comm->d.slot_bytes - comm->d.raw_bytes;
+  const bool ll = tp_use_ll() && (int64_t)T * dim * 4 <= comm->d.ll_bytes;
   if (ll) return (int)launch(tp_allreduce_kernel<true>, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
   return (int)launch(tp_allreduce_kernel<false>, dim3(grid), dim3(kTpThreads), smem, stream, true, a);
 }
@@ -243,6 +298,21 @@ int pk_tp_all_reduce_add_rms_norm(pk_tp_comm* comm, pk_bf16* hidden, const pk_bf
                                   int batch_size, float eps, pk_stream stream) {
   if (hidden_dim > 11000) return -1;  // row parked in shared memory as fp32
   return tp_launch(comm, partial, hidden, weight, out, hidden_dim, batch_size, eps, 1, stream);
+}
+
+int pk_tp_top1_exchange(pk_tp_comm* comm, const pk_bf16* local_max, int* index_inout, int batch_size, int vocab_offset,
+                        const uint32_t* step_counter, uint32_t seq_or_op, pk_stream stream) {
+  if (!comm || batch_size <= 0 || batch_size > 64 || comm->d.gll_bytes < 8192) return -1;
+  TpTop1Args a{};
+  a.d = comm->d;
+  a.vals = (const bf16*)local_max;
+  a.idx = index_inout;
+  a.bs = batch_size;
+  a.vocab_offset = vocab_offset;
+  a.entry0 = step_counter ? 0 : 64;  // graph-path and host-path calls never share a line
+  a.step = step_counter;
+  a.seq_arg = seq_or_op;
+  return (int)launch(tp_top1_exchange_kernel, dim3(1), dim3(64), 0, stream, true, a);
 }
 
 int64_t pk_tp_max_rows(pk_tp_comm* comm, int hidden_dim) {

@@ -94,6 +94,7 @@ EXT_SIGNATURES = {
     "pk_tp_comm_create": (vp, [i32, i32, C.POINTER(vp), C.POINTER(vp), i64]),
     "pk_tp_comm_destroy": (None, [vp]),
     "pk_tp_max_rows": (i64, [vp, i32]),
+    "pk_tp_top1_exchange": (i32, [vp, vp, vp, i32, i32, vp, C.c_uint32, vp]),
     "pk_tp_all_reduce": (i32, [vp, vp, i64, vp]),
     "pk_tp_all_reduce_rows": (i32, [vp, vp, i32, i32, vp]),
     "pk_tp_all_reduce_add_rms_norm": (i32, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),

@@ -70,6 +70,7 @@ def host_lib() -> C.CDLL:
         h.pq_bench_gemv_pass.argtypes = [vp, i32, vp, vp]
         h.pq_launches_per_step.restype = C.c_int64
         h.pq_launches_per_step.argtypes = [vp]
+        h.pq_logits_cols.argtypes = [vp, vp]
         h.pq_meta_bytes.restype = C.c_int64
         h.pq_meta_bytes.argtypes = [vp]
         h.pq_event_record.restype = vp
@@ -172,8 +173,25 @@ class Qwen3Model:
     def available_pages(self) -> int:
         return self._h.pq_available_pages(self._m)
 
+    def logits_shard(self) -> tuple[int, int]:
+        """(columns, first vocabulary id) of the logits rows this rank returns: the whole vocabulary, or -- on the
+        fused tensor-parallel path, where lm_head is vocab-sharded -- this rank's slice of it."""
+        off = C.c_int()
+        cols = self._h.pq_logits_cols(self._m, C.byref(off))
+        return int(cols), int(off.value)
+
+    def gather_logits(self, local: torch.Tensor, dist) -> torch.Tensor:
+        """Full-vocabulary rows from every rank's shard (test / parity plumbing over torch.distributed; the decode
+        path itself only exchanges each shard's (max, index))."""
+        cols, _ = self.logits_shard()
+        if cols == self.cfg.vocab_size or dist is None:
+            return local
+        parts = [torch.empty_like(local) for _ in range(self.rt.tensor_parallel.world_size)]
+        dist.all_gather(parts, local.contiguous())
+        return torch.cat(parts, dim=1)
+
     def _logits_view(self, ptr: int, rows: int) -> torch.Tensor:
-        out = torch.empty((rows, self.cfg.vocab_size), dtype=torch.bfloat16, device="cuda")
+        out = torch.empty((rows, self.logits_shard()[0]), dtype=torch.bfloat16, device="cuda")
         torch.cuda.current_stream().synchronize()
         self._ck(self._h.pq_copy_out(self._m, out.data_ptr(), ptr, out.numel() * 2))
         return out

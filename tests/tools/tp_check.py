@@ -114,7 +114,7 @@ def main():
     cpu_w = {} if rank == 0 else None
     m = Qwen3Model(cfg, broadcast_weights(cfg, rank, cpu_w), rt, tp_comm=comm2)
     kv = m.alloc_kv()
-    got = [bits(m.prefill([prompt], [kv])[0])]
+    got = [bits(m.gather_logits(m.prefill([prompt], [kv]), dist)[0])]
     if rank == 0:
         O.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
         orc = O.OracleQwen3(oracle_cfg(cfg), to_numpy_bits(cpu_w), tp_world=world, num_pages=pages)
@@ -127,8 +127,11 @@ def main():
             want.append(orc.decode([int(toks[i])], [okv])[0])
     dist.broadcast(toks, 0)
     for i in range(n_steps):
-        lg, _ = m.decode([int(toks[i])], [kv])
-        got.append(bits(lg[0]))
+        lg, sampled = m.decode([int(toks[i])], [kv])
+        full = m.gather_logits(lg, dist)
+        # the vocab-sharded greedy token (max/index exchange) must be the arg-max of the gathered row, lowest index on ties
+        ok &= int(sampled[0]) == int(full[0].float().argmax())
+        got.append(bits(full[0]))
     if rank == 0:
         worst = 0.0
         for i, (g_, w_) in enumerate(zip(got, want)):
