@@ -30,7 +30,10 @@ from tests.helpers import bits, logits_agree, oracle_cfg
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PK_SKIP_FULLSIZE") == "1", reason="PK_SKIP_FULLSIZE=1")]
 
-TOL_ULP = 8          # bf16 ulps at the row's max |logit| after 36 layers (measured <= ~3; see profiles/README.md)
+# bf16 ulps at the row's max |logit| after 36 layers.  Measured on B200 (gpurun_out/c1_pytest.log, profiles/README.md):
+# fused 7.4 worst over 65 steps of config 1, 5.4 on config 2; compat 5.9 / 5.0 -- rounding-point flips accumulate as
+# ~sqrt(layers) (the 2-4 layer configs of test_model_gpu.py sit at <= 2 with a bound of 6).  12 = 1.6 x the worst seen.
+TOL_ULP = 12
 CFG1_STEPS = int(os.environ.get("PK_FULLSIZE_STEPS", "64"))
 
 
@@ -69,7 +72,13 @@ def _teacher_forced(m, prompt, tokens):
     return got
 
 
-@pytest.mark.parametrize("name,kw,steps", [("fused", dict(fused=True), None), ("compat", dict(fused=False), 16)])
+REF_LIB = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libkernels_ref.so"))
+CFG1_VARIANTS = [("fused", dict(fused=True), None), ("compat", dict(fused=False), 16)]
+if os.path.exists(REF_LIB):  # the reference's own CUDA kernels under the same host: how far THEY sit from the oracle
+    CFG1_VARIANTS.append(("refkernels", dict(fused=False, kernel_lib=REF_LIB), 16))
+
+
+@pytest.mark.parametrize("name,kw,steps", CFG1_VARIANTS)
 def test_qwen3_4b_config1_vs_live_oracle(w4b, cfg1_oracle, name, kw, steps):
     want, toks = cfg1_oracle
     n = len(toks) if steps is None else min(steps, len(toks))
