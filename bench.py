@@ -343,14 +343,15 @@ def run_ours(args, cfg, rank, world, dist):
         tp1_model = Qwen3Model(cfg, None, ModelRuntimeConfig(enable_cuda_graph=True, device_ordinal=local_rank, fused=True,
                                                             num_pages=pages, max_batch=1, enable_pdl=True))
     keep_cpu = {} if (world == 1 and rank == 0) else None
-    gen = iter_random_weights(cfg, seed=0, device="cpu") if rank == 0 else None
+    on_gpu = args.weights == "cuda"
+    gen = iter_random_weights(cfg, seed=0, device="cuda" if on_gpu else "cpu") if (rank == 0 or on_gpu) else None
     for name, shape in weight_shapes(cfg).items():
-        if rank == 0:
+        if rank == 0 or on_gpu:
             n2, t = next(gen)
             assert n2 == name
             if keep_cpu is not None:
-                keep_cpu[name] = t
-        if world > 1:
+                keep_cpu[name] = t.cpu() if on_gpu else t
+        if world > 1 and not on_gpu:
             d = t.cuda() if rank == 0 else torch.empty(shape, dtype=torch.bfloat16, device="cuda")
             dist.broadcast(d, 0)
             t = d
@@ -462,7 +463,8 @@ def run_ours(args, cfg, rank, world, dist):
                            "parallelism": f"tp{world}", "cuda_graph": True, "pdl": True,
                            "lm_head": "vocab-sharded (max/index exchange)" if lm_rows != cfg.vocab_size else "full",
                            "tp_collective": (os.environ.get("PK_TP_MODE", "ll") + " (GEMV-fused LL all-reduce over NVLink peer memory)") if world > 1 else None,
-                           "checkpoint": "random-init N(0, 0.02), seed 0, generated on the CPU (the oracle fixtures' checkpoint)",
+                           "checkpoint": "random-init N(0, 0.02), seed 0, generated on the CPU (the oracle fixtures' checkpoint)"
+                           if not on_gpu else "random-init N(0, 0.02), seed 0, CUDA generator (tuning run: NOT the fixtures' checkpoint)",
                            "decode_impl": "persistent single-launch step" if persistent else "fused multi-kernel graph",
                            "launches_per_step": launches_per_step, "model_load_s": round(load_s, 1)},
                 "ttft_ms": ttft_ms, "ttft_prompt_len": prompt_len,
@@ -582,6 +584,9 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-tp-base", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the side legs (cpu_baseline, gpu_reference, tp_base / tp1)")
+    ap.add_argument("--weights", default="cpu", choices=["cpu", "cuda"],
+                    help="cpu (default): the seed-0 CPU checkpoint the oracle fixtures were computed on; cuda: generated on "
+                         "each GPU (fast; tuning sweeps only -- the parity key then reports a different checkpoint)")
     args = ap.parse_args()
     if args.quick:
         args.no_cpu_baseline = args.no_gpu_reference = args.no_tp_base = True

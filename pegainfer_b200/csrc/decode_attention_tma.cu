@@ -78,6 +78,21 @@ __device__ __forceinline__ void t_st_cluster(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void t_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrive (release, cluster scope) on an mbarrier that lives in another CTA of the cluster
+__device__ __forceinline__ void t_mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool t_mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void t_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void t_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -159,6 +174,7 @@ decode_attention_tma_kernel(const __grid_constant__ CUtensorMap map_k, const __g
   bf16* k_s = q_s + T_GROUP * T_HD;
   bf16* v_s = k_s + T_HD;
   uint64_t* full = reinterpret_cast<uint64_t*>(v_s + T_HD);               // [nslot]
+  uint64_t* merged = full + T_MAX_SLOTS;                                  // leaders: all CTAs' states have landed
   float* st_o = reinterpret_cast<float*>(tiles);                          // [8][4][128] (after the page loop)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,6 +185,11 @@ decode_attention_tma_kernel(const __grid_constant__ CUtensorMap map_k, const __g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nslot; ++s) mbar_init(full + s, 1);
+    // one arrival per (head this CTA leads, source CTA, source warp of the 4 that carry that head's 128 dims)
+    const int heads_led = rank < T_GROUP ? (T_GROUP - rank + cs - 1) / cs : 0;
+    mbar_init(merged, (uint32_t)max(1, heads_led * cs * 4));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     mbar_fence_init();
   }
   t_cluster_arrive();  // opening cluster barrier: completed (t_cluster_wait) before the first remote store
@@ -240,10 +261,12 @@ decode_attention_tma_kernel(const __grid_constant__ CUtensorMap map_k, const __g
   const int k_tok = ((lm_i >> 1) << 3) + lm_r, k_c = lm_i & 1;   // K: matrices {tok 0-7 lo, tok 0-7 hi, tok 8-15 lo, tok 8-15 hi}
   const int v_tok = ((lm_i & 1) << 3) + lm_r, v_c = lm_i >> 1;   // V: {tok 0-7 | tok 8-15} x {dims 8d | 8(d+1)}
 
-  for (int lp = 0; lp < my_pages; ++lp) {
-    const int slot = lp % nslot;
-    if ((slot & (T_WARPS - 1)) != warp) continue;  // a slot is consumed by one warp only, in page order
-    t_wait_or_trap(full + slot, (uint32_t)((lp / nslot) & 1));
+  // a slot is consumed by ONE warp (slot & 7), in page order: walk the ring passes, then this warp's slots
+  for (int base = 0, pass = 0; base < my_pages; base += nslot, ++pass)
+  for (int slot = warp; slot < nslot; slot += T_WARPS) {
+    const int lp = base + slot;
+    if (lp >= my_pages) break;
+    t_wait_or_trap(full + slot, (uint32_t)(pass & 1));
     uint8_t* tile = tiles + (size_t)slot * T_SLOT;
     const int gp = p_lo + lp;
     if (lp == pos_lp) {  // patch the step's own row into the tile (the TMA saw the slot before it was written)
@@ -368,11 +391,16 @@ decode_attention_tma_kernel(const __grid_constant__ CUtensorMap map_k, const __g
         t_st_cluster(t_map_rank(smem_u32(c_m + entry), leader), mx);
         t_st_cluster(t_map_rank(smem_u32(c_d + entry), leader), dd);
       }
+      // this warp's 32 dims of head h are in flight to the leader: one release-arrive on its mbarrier
+      __syncwarp();
+      if (lane == 0) t_mbar_arrive_remote(t_map_rank(smem_u32(merged), leader));
     }
   }
-  t_cluster_arrive();
-  t_cluster_wait();
-  if (rank >= T_GROUP || threadIdx.x >= T_HD) return;
+  // Only the head leaders wait (their shared memory is the landing zone); every other CTA is done.
+  if (rank >= T_GROUP || rank >= cs) return;
+  for (uint32_t spins = 0; !t_mbar_try_wait_cluster(merged, 0); ++spins)
+    if (spins > (1u << 26)) __trap();
+  if (threadIdx.x >= T_HD) return;
   for (int h = rank; h < T_GROUP; h += cs) {  // this CTA leads heads rank, rank + cs, ...
     const int e0 = (h / cs) * cs;
     float mx = -INFINITY;
@@ -413,7 +441,7 @@ size_t tma_attn_smem(int nslot) {
 
 struct TmaAttnConfig {
   int nslot = 10;
-  int max_cluster = 16;
+  int max_cluster = 8;   // 16 (non-portable) measured +4.4 us per launch on B200: opt-in via PK_ATTN_CLUSTER=16
   bool ready = false, ok = false;
 };
 

@@ -19,7 +19,7 @@ class GemvArgs(C.Structure):
     """pk_b200_gemv_args (include/pegainfer_kernels.h)."""
     _fields_ = [("W", vp), ("X", vp), ("Y", vp * 3), ("seg_rows", i32 * 3), ("M", i32), ("N", i32),
                 ("K", i32), ("x_mode", i32), ("residual", vp), ("norm_w", vp), ("eps", f32),
-                ("hidden_out", vp), ("normed_out", vp), ("epi", i32), ("tp_comm", vp)]
+                ("hidden_out", vp), ("normed_out", vp), ("epi", i32), ("tp_comm", vp), ("tp_step", vp), ("tp_op", i32)]
 
 
 class PrefetchSpan(C.Structure):

@@ -614,3 +614,78 @@ def test_prefill_attention_tc(starts, lens, nq, nkv):
     assert lib.pk_b200_prefill_attention_tc(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
                                             p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(q_indptr)), nq, nkv, hd, 32,
                                             T, bs, L.page_stride, sm, stream()) == -1  # page size 32: unsupported
+
+
+# ------------------------------------------------------------------ tensor-parallel collectives, two "ranks" on ONE GPU
+def _two_rank_comms(lib, staging_bytes=1 << 20):
+    """Two communicators of a world of 2 whose staging / flag buffers all live on this GPU: the peer-memory protocols
+    (posted stores + sequence-stamped lines) run unchanged, the 'NVLink' writes are local.  The two ranks' kernels must be
+    co-resident (they wait for each other), so callers keep the grids small and use two streams."""
+    import ctypes as C
+    stage = [torch.zeros(staging_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    flags = [torch.zeros(int(lib.pk_tp_flag_bytes()), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    sp = (C.c_void_p * 2)(stage[0].data_ptr(), stage[1].data_ptr())
+    fp = (C.c_void_p * 2)(flags[0].data_ptr(), flags[1].data_ptr())
+    comms = [lib.pk_tp_comm_create(r, 2, sp, fp, staging_bytes) for r in range(2)]
+    assert all(comms)
+    _keep.extend(stage + flags)
+    return comms
+
+
+@pytest.mark.parametrize("N", [1, 3])
+def test_gemv_ll_allreduce_two_ranks_one_gpu(N):
+    """epi 3: GEMV + all-reduce of the CTA's own rows in one kernel.  Each 'rank' holds a column slice of W and the
+    matching slice of x (row-parallel o_proj / down_proj); both must write the rank-ordered bf16 sum of the two bf16
+    partials, bit-identical to the oracle's all-reduce model, for two consecutive ops (slot / sequence reuse)."""
+    lib = get_lib("b200")
+    import ctypes as C
+    M, K = 512, 1024  # 64 CTAs per rank: both grids are resident at once
+    comms = _two_rank_comms(lib)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    step = torch.tensor([7], dtype=torch.int32, device="cuda")
+    for op in range(3):
+        W, x = rnd((M, 2 * K), 70 + op, 0.05), rnd((N, 2 * K), 80 + op, 1.0)
+        parts, outs = [], []
+        torch.cuda.synchronize()
+        for r in range(2):
+            Wr = dev(W[:, r * K:(r + 1) * K].contiguous())
+            xr = dev(x[:, r * K:(r + 1) * K].contiguous())
+            y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
+            g = ffi.GemvArgs()
+            g.W, g.X = p(Wr), p(xr)
+            g.Y = (C.c_void_p * 3)(y.data_ptr(), None, None)
+            g.seg_rows = (C.c_int * 3)(M, 0, 0)
+            g.M, g.N, g.K, g.x_mode, g.epi = M, N, K, 0, 3
+            g.tp_comm, g.tp_step, g.tp_op = comms[r], step.data_ptr(), op
+            with torch.cuda.stream(streams[r]):
+                assert lib.pk_b200_gemv_fused(C.byref(g), streams[r].cuda_stream) == 0
+            outs.append(y)
+            parts.append(O.gemm(bits(W[:, r * K:(r + 1) * K].contiguous()), bits(x[:, r * K:(r + 1) * K].contiguous())))
+        torch.cuda.synchronize()
+        want = O.all_reduce_sum(parts)
+        assert (bits(outs[0]) == bits(outs[1])).all(), "ranks disagree"
+        assert_bf16_close(bits(outs[0]), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what=f"ll all-reduce op {op}")
+
+
+def test_tp_top1_exchange_two_ranks_one_gpu():
+    """Vocab-sharded greedy token: every rank ends with the same global (max, lowest index) winner."""
+    lib = get_lib("b200")
+    comms = _two_rank_comms(lib)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    step = torch.tensor([3], dtype=torch.int32, device="cuda")
+    vals = [from_bits(O.f32_to_bf16(np.array(v, np.float32)), "cuda") for v in ([1.5, 9.0, 2.0], [4.0, 9.0, -1.0])]
+    idx = [torch.tensor(i, dtype=torch.int32, device="cuda") for i in ([10, 20, 30], [5, 6, 7])]
+    torch.cuda.synchronize()
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            assert lib.pk_tp_top1_exchange(comms[r], p(vals[r]), p(idx[r]), 3, r * 1000, step.data_ptr(), 250, streams[r].cuda_stream) == 0
+    torch.cuda.synchronize()
+    # request 0: rank 1 wins (4.0 at 1000+5); request 1: tie at 9.0 -> lowest global index (rank 0: 20); request 2: rank 0 (30)
+    assert idx[0].tolist() == idx[1].tolist() == [1005, 20, 30]
+    # host-path sequence numbers (no step counter) use separate lines
+    idx2 = [torch.tensor([3], dtype=torch.int32, device="cuda"), torch.tensor([4], dtype=torch.int32, device="cuda")]
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            assert lib.pk_tp_top1_exchange(comms[r], p(vals[r]), p(idx2[r]), 1, r * 1000, None, 0x80000001, streams[r].cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert idx2[0].tolist() == idx2[1].tolist() == [1004]
