@@ -186,6 +186,11 @@ void pk_b200_set_pdl(int enable);
 int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16* const* Y, const int* seg_rows, int M, int N,
                           int K, pk_stream stream);
 
+/* gate_up projection + SwiGLU in one tensor-core launch (CTA-pair kernel): W = [gate (M rows); up (M rows)] x [K],
+ * Y[tok][M] = bf16(silu(bf16(gate.x)) * bf16(up.x)) -- gemm_cuda + silu_mul_fused_cuda with the same rounding points.
+ * Returns 0, or -2 when the shape is not for this kernel (run the two-kernel sequence instead). */
+int pk_b200_gemm_swiglu(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K, pk_stream stream);
+
 /* GEMV with fused prologue/epilogue for decode (N == 1..4 tokens), one launch:
  *   x_mode 0: x = X as is ([N, K]).
  *   x_mode 1: X is `hidden` [N, K]; x = RMSNorm(hidden + residual) * norm_w computed in the

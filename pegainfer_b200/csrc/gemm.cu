@@ -263,6 +263,17 @@ static int gemm_impl_mode() {  // 0 tcgen05 (default), 1 simt
 
 void launch_gemm_seg(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K,
                      cudaStream_t stream);
+// gemm2.cu: the CTA-pair kernel (tcgen05.mma.cta_group::2); -2 = not for this shape
+int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K, int swiglu,
+                     cudaStream_t stream);
+static bool gemm_pair_enabled() {  // PK_GEMM_PAIR=0 keeps the round-1 single-CTA kernel for A/B runs
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_PAIR");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void launch_gemm(const bf16* W, const bf16* X, bf16* Y, int M, int N, int K, cudaStream_t stream) {
   launch_gemm_seg(W, X, Y, Y, Y, M, M, M, N, K, stream);
@@ -273,6 +284,9 @@ void launch_gemm_seg(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
   if (M <= 0 || N <= 0 || K <= 0) return;
   const bool tma_ok = K % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  if (tma_ok && gemm_impl_mode() == 0 && gemm_pair_enabled() &&
+      launch_gemm_pair(W, X, Y, Y1, Y2, e0, e1, M, N, K, 0, stream) == 0)
+    return;
   if (tma_ok && gemm_impl_mode() == 0) {
     // Tile width by wave count: tiles = ceil(N/128) * ceil(M/BN) on `sms` persistent CTAs; cost ~ waves * (BN + c).
     // M = 2560 outputs (o_proj / down_proj of Qwen3-4B) at 2048 tokens: BN 256 -> 160 tiles = 2 waves of 256-wide
@@ -329,6 +343,15 @@ extern "C" int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16
   pk::launch_gemm_seg((const pk::bf16*)W, (const pk::bf16*)X, (pk::bf16*)Y[0], (pk::bf16*)(Y[1] ? Y[1] : Y[0]),
                       (pk::bf16*)(Y[2] ? Y[2] : Y[0]), seg_rows[0], seg_rows[0] + seg_rows[1], M, N, K, stream);
   return 0;
+}
+
+// gate_up projection with the SwiGLU activation folded into the epilogue: W = [gate (M rows); up (M rows)] x [K],
+// Y[tok][M] = bf16(silu(bf16(gate.x)) * bf16(up.x)) -- gemm + silu_mul_fused_cuda of the reference in one launch, same
+// rounding points.  Returns -2 when the CTA-pair kernel cannot take the shape (caller runs the two-kernel sequence).
+extern "C" int pk_b200_gemm_swiglu(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K, pk_stream stream) {
+  if (!W || !X || !Y || M <= 0 || N <= 0 || K <= 0) return -1;
+  if (!pk::gemm_pair_enabled() || pk::gemm_impl_mode() != 0) return -2;
+  return pk::launch_gemm_pair((const pk::bf16*)W, (const pk::bf16*)X, (pk::bf16*)Y, (pk::bf16*)Y, (pk::bf16*)Y, M, M, M, N, K, 1, stream);
 }
 
 // Same dispatch as gemm_graphsafe_cuda (gemv.cu): N <= 4 streams the weights (HBM-bound GEMV), larger N runs on the

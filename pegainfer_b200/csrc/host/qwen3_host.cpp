@@ -34,7 +34,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused) PQ_OPT(pk_b200_gemm_segments)
   PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
-  PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid) PQ_OPT(pk_tp_top1_exchange)
+  PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid) PQ_OPT(pk_tp_top1_exchange) PQ_OPT(pk_b200_gemm_swiglu)
 #undef PQ_REQ
 #undef PQ_OPT
   if (!missing.empty()) return "kernel library " + p + " lacks:" + missing;
@@ -674,8 +674,13 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
     if (!all_reduce_hidden(ob.data.bf(), H, T)) return false;
     k.fused_add_rms_norm_batched_cuda(hcur, ob.data.bf(), L.post_attention_layernorm.data.bf(), nrm.data.bf(), H, T,
                                       eps, st);
-    k.gemm_cuda(L.mlp.gate_up_proj.data.bf(), nrm.data.bf(), gu.data.bf(), 2 * I, T, H, st);
-    k.silu_mul_fused_cuda(gu.data.bf(), act.data.bf(), I, T, st);
+    // gate_up GEMM with the SwiGLU activation in its epilogue (one launch, same rounding points) when the kernel
+    // library offers it and takes the shape; else the reference's two launches
+    if (!(rt.mode >= 1 && k.pk_b200_gemm_swiglu &&
+          k.pk_b200_gemm_swiglu(L.mlp.gate_up_proj.data.bf(), nrm.data.bf(), act.data.bf(), I, T, H, st) == 0)) {
+      k.gemm_cuda(L.mlp.gate_up_proj.data.bf(), nrm.data.bf(), gu.data.bf(), 2 * I, T, H, st);
+      k.silu_mul_fused_cuda(gu.data.bf(), act.data.bf(), I, T, st);
+    }
     k.gemm_cuda(L.mlp.down_proj.data.bf(), act.data.bf(), ob.data.bf(), H, T, I, st);
     if (!all_reduce_hidden(ob.data.bf(), H, T)) return false;
     k.add_cuda(hcur, ob.data.bf(), hnext, H * T, st);  // prefill.rs:183 (rounds the residual sum)

@@ -43,7 +43,7 @@ struct KernelLib {
   PQ_FN(pk_b200_launch_count) PQ_FN(pk_b200_set_pdl) PQ_FN(pk_b200_gemv_fused) PQ_FN(pk_b200_gemm_segments)
   PQ_FN(pk_b200_decode_attention_fused) PQ_FN(pk_b200_decode_step_persistent) PQ_FN(pk_tp_all_reduce_rows)
   PQ_FN(pk_tp_all_reduce_add_rms_norm) PQ_FN(pk_tp_max_rows)
-  PQ_FN(pk_b200_decode_attention_fused_prefetch) PQ_FN(pk_b200_gemv_grid) PQ_FN(pk_tp_top1_exchange)
+  PQ_FN(pk_b200_decode_attention_fused_prefetch) PQ_FN(pk_b200_gemv_grid) PQ_FN(pk_tp_top1_exchange) PQ_FN(pk_b200_gemm_swiglu)
 #undef PQ_FN
   bool has_extensions() const { return pk_b200_gemv_fused != nullptr; }
   std::string load(const std::string& p);  // returns error text, empty on success

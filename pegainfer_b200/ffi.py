@@ -81,6 +81,7 @@ EXT_SIGNATURES = {
     "pk_b200_version": (C.c_char_p, []),
     "pk_b200_launch_count": (i64, [i32]),
     "pk_b200_set_pdl": (None, [i32]),
+    "pk_b200_gemm_swiglu": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "pk_b200_gemm_segments": (i32, [vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
     "pk_b200_gemv_fused": (i32, [C.POINTER(GemvArgs), vp]),
     "pk_b200_set_gemv_tuning": (None, [i32, i32, i32]),

@@ -193,7 +193,9 @@ def test_gemv_multi_token(lib, N):
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 128, 2560), (2560, 77, 4096), (1000, 130, 576), (4096, 300, 2560),
-                                   (19456, 128, 2560), (64, 8, 64), (24, 16, 40)])
+                                   (19456, 128, 2560), (64, 8, 64), (24, 16, 40),
+                                   # CTA-pair kernel (N > 128): full + ragged token / feature tiles, several K depths
+                                   (2560, 512, 4096), (6144, 257, 2560), (2560, 1024, 9728), (136, 129, 64), (19456, 2048, 2560)])
 def test_gemm(lib, M, N, K):
     W, X = rnd((M, K), 17, 0.02), rnd((N, K), 18, 1.0)
     Y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
@@ -202,6 +204,21 @@ def test_gemm(lib, M, N, K):
     want = O.gemm(bits(W), bits(X))
     assert_bf16_close(bits(Y), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9,
                       what=f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("inter,N,K", [(9728, 512, 2560), (1000, 300, 576), (128, 129, 64)])
+def test_gemm_swiglu_epilogue(inter, N, K):
+    """gate_up GEMM with SwiGLU in the epilogue == gemm + silu_mul_fused (oracle composition, prefill.rs:168-176)."""
+    lib = get_lib("b200")
+    W, X = rnd((2 * inter, K), 27, 0.03), rnd((N, K), 28, 1.0)
+    act = torch.zeros((N, inter), dtype=torch.bfloat16, device="cuda")
+    rc = lib.pk_b200_gemm_swiglu(p(dev(W)), p(dev(X)), p(act), inter, N, K, stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = O.silu_mul_fused(O.gemm(bits(W), bits(X)), inter)
+    assert_bf16_close(bits(act), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what=f"gemm+swiglu {inter}x{N}x{K}")
+    # one token tile is not a pair problem: the entry says so and the caller falls back
+    assert lib.pk_b200_gemm_swiglu(p(dev(W)), p(dev(X)), p(act), inter, 64, K, stream()) == -2
 
 
 def test_gemm_graphsafe_batch_bucket(lib):  # decode bucket > 4 goes to the tensor-core path

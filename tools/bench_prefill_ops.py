@@ -38,6 +38,23 @@ for T in (128, 2048):
         ref = timeit(lambda: torch.matmul(X, W.t()))
         fl = 2.0 * M * T * K
         print(f"gemm {name:8s} M={M:6d} K={K:5d}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s   (torch/cuBLAS {ref*1e3:8.1f} us {fl/ref/1e9:7.1f})")
+    # gate_up + SwiGLU: one launch (pair kernel epilogue) vs gemm + silu_mul_fused
+    I, H = 9728, 2560
+    W = (torch.randn((2 * I, H), device="cuda") * 0.02).to(torch.bfloat16)
+    X = torch.randn((T, H), device="cuda").to(torch.bfloat16)
+    gu = torch.empty((T, 2 * I), device="cuda", dtype=torch.bfloat16)
+    act = torch.empty((T, I), device="cuda", dtype=torch.bfloat16)
+    if lib.pk_b200_gemm_swiglu(W.data_ptr(), X.data_ptr(), act.data_ptr(), I, T, H, st) == 0:
+        ms1 = timeit(lambda: lib.pk_b200_gemm_swiglu(W.data_ptr(), X.data_ptr(), act.data_ptr(), I, T, H, st))
+    else:
+        ms1 = float("nan")
+    def two():
+        lib.gemm_cuda(W.data_ptr(), X.data_ptr(), gu.data_ptr(), 2 * I, T, H, st)
+        lib.silu_mul_fused_cuda(gu.data_ptr(), act.data_ptr(), I, T, st)
+    ms2 = timeit(two)
+    fl = 2.0 * 2 * I * T * H
+    print(f"gate_up+SwiGLU fused: {ms1*1e3:8.1f} us {fl/ms1/1e9:7.1f} TFLOP/s   gemm + silu_mul: {ms2*1e3:8.1f} us")
+    del W, X, gu, act
     # attention: one layer, nq 32 nkv 8
     nq, nkv, hd = 32, 8, 128
     pages = T // 16 + 1
