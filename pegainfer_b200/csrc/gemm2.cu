@@ -94,12 +94,19 @@ struct G2Args {
   int swiglu;     // 1: W = [gate (M rows); up (M rows)], Y[tok][M] = silu(gate) * up
 };
 
-template <int BN, int STAGES>
+// A pair tile is 256 tokens x (NSUB * BN) features: NSUB accumulators of BN columns side by side in TMEM, one
+// tcgen05.mma per accumulator per K step (NSUB = 2, BN = 160: the 320-wide tile that turns the 2560-feature
+// projections of Qwen3-4B into ONE wave of 64 tiles on 74 pairs instead of two waves of 256-wide tiles).
+template <int BN, int NSUB, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const G2Args a) {
-  constexpr int HB = BN / 2;  // B rows (features) staged per CTA
-  constexpr int A_BYTES = G2_BM * G2_BK * 2, B_BYTES = HB * G2_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  constexpr int HB = BN / 2;          // B rows (features) staged per CTA per accumulator
+  constexpr int TN = NSUB * BN;       // features per tile
+  constexpr int A_BYTES = G2_BM * G2_BK * 2, B_SUB = HB * G2_BK * 2, B_BYTES = NSUB * B_SUB, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int NBUF = (2 * TN <= 512) ? 2 : 1;  // TMEM accumulator buffers
+  constexpr uint32_t TMEM_COLS = (NBUF * TN <= 256) ? 256 : 512;
+  static_assert(B_SUB % 1024 == 0, "each B sub-tile must start on a swizzle-atom boundary");
+  static_assert(NSUB == 1 || TN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t g2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);  // used in the leader
@@ -113,7 +120,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const bool leader = rank == 0;
   const int M = a.M, N = a.N, K = a.K;
   const int m_tiles = (N + 2 * G2_BM - 1) / (2 * G2_BM);  // pair tiles along tokens
-  const int n_tiles = a.swiglu ? (M + HB - 1) / HB : (M + BN - 1) / BN;
+  const int n_tiles = a.swiglu ? (M + HB - 1) / HB : (M + TN - 1) / TN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + G2_BK - 1) / G2_BK;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -146,7 +153,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int mb = tile % m_tiles, nb = tile / m_tiles;
         const int tok0 = mb * 2 * G2_BM + (int)rank * G2_BM;
         // this CTA's B rows: its half of the BN features, or (SwiGLU) the gate block (leader) / up block (peer)
-        const int wrow0 = a.swiglu ? (int)rank * M + nb * HB : nb * BN + (int)rank * HB;
+        const int wrow0 = a.swiglu ? (int)rank * M + nb * HB : nb * TN + (int)rank * HB;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           g2_wait(empty + s, (uint32_t)(((it / STAGES) & 1) ^ 1));
@@ -154,7 +161,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (leader) mbar_expect_tx(full + s, 2 * STAGE_BYTES);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           g2_tma_2d(st, &map_x, kb * G2_BK, tok0, fb);
-          g2_tma_2d(st + A_BYTES, &map_w, kb * G2_BK, wrow0, fb);
+#pragma unroll
+          for (int j = 0; j < NSUB; ++j) g2_tma_2d(st + A_BYTES + j * B_SUB, &map_w, kb * G2_BK, wrow0 + j * BN, fb);
         }
       }
     }
@@ -164,10 +172,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int it = 0, lt = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
-        const int as = lt & 1;
-        g2_wait(tempty + as, (uint32_t)(((lt >> 1) & 1) ^ 1));
+        const int as = lt % NBUF;
+        g2_wait(tempty + as, (uint32_t)(((lt / NBUF) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TN);
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           g2_wait(full + s, (uint32_t)((it / STAGES) & 1));
@@ -175,10 +183,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (lane == 0) {
             const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
             const uint64_t adesc = make_sw128_desc(a_addr);
-            const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES);
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              g2_umma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < NSUB; ++j)
+                g2_umma(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(k * 2),
+                        make_sw128_desc(a_addr + A_BYTES + j * B_SUB) + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             g2_commit_both(empty + s);
             if (kb == k_blocks - 1) g2_commit_both(tfull + as);
           }
@@ -194,11 +204,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     int lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
       const int mb = tile % m_tiles, nb = tile / m_tiles;
-      const int as = lt & 1;
-      g2_wait(tfull + as, (uint32_t)((lt >> 1) & 1));
+      const int as = lt % NBUF;
+      g2_wait(tfull + as, (uint32_t)((lt / NBUF) & 1));
       tc_fence_after();
       const int tok = mb * 2 * G2_BM + (int)rank * G2_BM + q * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN);
       if (a.swiglu) {
         // columns [0, HB) = gate, [HB, BN) = up of features nb*HB + c
 #pragma unroll 1
@@ -233,10 +243,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < TN; c += 32) {
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)c, v);
-          const int f0 = nb * BN + c;
+          const int f0 = nb * TN + c;
           if (tok < N && f0 < M) {
             bf16* dst;
             if (f0 < a.e0) dst = a.Y + (size_t)tok * a.e0 + f0;
@@ -288,17 +298,17 @@ bool g2_make_map(CUtensorMap* map, const void* base, int rows, int K, int box_ro
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int BN, int NSUB, int STAGES>
 cudaError_t g2_launch(const CUtensorMap& mx, const CUtensorMap& mw, const G2Args& a, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (G2_BM * G2_BK * 2 + (BN / 2) * G2_BK * 2) + 1024 + 256;
-  auto kern = gemm_tc2_kernel<BN, STAGES>;
+  constexpr size_t smem = (size_t)STAGES * (G2_BM * G2_BK * 2 + NSUB * (BN / 2) * G2_BK * 2) + 1024 + 256;
+  auto kern = gemm_tc2_kernel<BN, NSUB, STAGES>;
   static thread_local bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cudaErrorInvalidValue;
     configured = true;
   }
   const int m_tiles = (a.N + 2 * G2_BM - 1) / (2 * G2_BM);
-  const int n_tiles = a.swiglu ? (a.M + BN / 2 - 1) / (BN / 2) : (a.M + BN - 1) / BN;
+  const int n_tiles = a.swiglu ? (a.M + BN / 2 - 1) / (BN / 2) : (a.M + NSUB * BN - 1) / (NSUB * BN);
   const int tiles = m_tiles * n_tiles;
   int pairs = sm_count() / 2;
   if (pairs > tiles) pairs = tiles;
@@ -316,25 +326,38 @@ int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
   G2Args a{Y, Y1, Y2, e0, e1, M, N, K, swiglu};
   CUtensorMap mx, mw;
   if (!g2_make_map(&mx, X, N, K, G2_BM)) return -2;
-  // tile width by wave count on sms/2 pairs (same cost model as gemm.cu)
+  // Tile choice by wave count (cost ~ waves x (tile width + epilogue)), in the units of gemm.cu's model: a pair tile
+  // of 256 tokens on sms/2 pairs costs what a 128-token tile of the same width costs on sms single CTAs.
   const int pairs = sm_count() / 2;
   const long m_tiles = (N + 2 * G2_BM - 1) / (2 * G2_BM);
-  int best = 256;
+  struct Cand { int bn, nsub; };
+  const Cand cands[3] = {{256, 1}, {160, 2}, {128, 1}};
+  int best = -1;
   long best_cost = -1;
-  const int cands[2] = {256, 128};
-  for (int ci = 0; ci < 2; ++ci) {
-    const int bn = cands[ci];
-    const long nt = swiglu ? (M + bn / 2 - 1) / (bn / 2) : (M + bn - 1) / bn;
+  for (int ci = 0; ci < (swiglu ? 1 : 3); ++ci) {
+    const int tn = cands[ci].bn * cands[ci].nsub;
+    const long nt = swiglu ? (M + cands[ci].bn / 2 - 1) / (cands[ci].bn / 2) : (M + tn - 1) / tn;
     const long waves = (m_tiles * nt + pairs - 1) / pairs;
-    const long cost = waves * (bn + 32);
+    const long cost = waves * (tn + 32);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
-      best = bn;
+      best = ci;
+    }
+  }
+  if (!swiglu) {  // is the single-CTA kernel (gemm.cu: 128-token tiles of width 256 / 160 / 128 on every SM) strictly better?
+    const long m1 = (N + G2_BM - 1) / G2_BM;
+    const int w1[3] = {256, 160, 128};
+    for (int i = 0; i < 3; ++i) {
+      const long waves = (m1 * ((M + w1[i] - 1) / w1[i]) + sm_count() - 1) / sm_count();
+      if (waves * (w1[i] + 32) < best_cost) return -2;
     }
   }
   const int rows_w = swiglu ? 2 * M : M;
-  if (!g2_make_map(&mw, W, rows_w, K, best / 2)) return -2;
-  cudaError_t e = best == 256 ? g2_launch<256, 6>(mx, mw, a, stream) : g2_launch<128, 8>(mx, mw, a, stream);
+  if (!g2_make_map(&mw, W, rows_w, K, cands[best].bn / 2)) return -2;
+  cudaError_t e;
+  if (best == 0) e = g2_launch<256, 1, 6>(mx, mw, a, stream);
+  else if (best == 1) e = g2_launch<160, 2, 5>(mx, mw, a, stream);
+  else e = g2_launch<128, 1, 8>(mx, mw, a, stream);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

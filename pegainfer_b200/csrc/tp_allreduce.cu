@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(64) tp_top1_exchange_kernel(const TpTop1Args a
     uint32_t spins = 0;
     do {
       asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "l"(line) : "memory");
-      if (++spins > (1u << 24)) __trap();
+      if (++spins > (1u << 26)) __trap();
     } while (l.z != seq || l.w != seq);
     const float ov = __uint_as_float(l.x);
     const int oi = (int)l.y;

@@ -195,7 +195,9 @@ def test_gemv_multi_token(lib, N):
 @pytest.mark.parametrize("M,N,K", [(512, 128, 2560), (2560, 77, 4096), (1000, 130, 576), (4096, 300, 2560),
                                    (19456, 128, 2560), (64, 8, 64), (24, 16, 40),
                                    # CTA-pair kernel (N > 128): full + ragged token / feature tiles, several K depths
-                                   (2560, 512, 4096), (6144, 257, 2560), (2560, 1024, 9728), (136, 129, 64), (19456, 2048, 2560)])
+                                   (2560, 512, 4096), (6144, 257, 2560), (2560, 1024, 9728), (136, 129, 64), (19456, 2048, 2560),
+                                   # 320-wide pair tiles (two 160-column accumulators): one wave for 2560 features at 2048 tokens
+                                   (2560, 2048, 1024), (2400, 2047, 320)])
 def test_gemm(lib, M, N, K):
     W, X = rnd((M, K), 17, 0.02), rnd((N, K), 18, 1.0)
     Y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
@@ -216,7 +218,8 @@ def test_gemm_swiglu_epilogue(inter, N, K):
     assert rc == 0
     torch.cuda.synchronize()
     want = O.silu_mul_fused(O.gemm(bits(W), bits(X)), inter)
-    assert_bf16_close(bits(act), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what=f"gemm+swiglu {inter}x{N}x{K}")
+    # gate and up are each within 1 ulp of the oracle after their bf16 rounding; silu(g) * u compounds them
+    assert_bf16_close(bits(act), want, 3, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what=f"gemm+swiglu {inter}x{N}x{K}")
     # one token tile is not a pair problem: the entry says so and the caller falls back
     assert lib.pk_b200_gemm_swiglu(p(dev(W)), p(dev(X)), p(act), inter, 64, K, stream()) == -2
 
