@@ -48,11 +48,19 @@ try:
     _HOST_THREADS = len(os.sched_getaffinity(0))
 except Exception:
     _HOST_THREADS = os.cpu_count() or 1
-# The CPU arm's OpenMP runtime reads these when the oracle library is first loaded: one thread per hardware thread,
-# bound in place (reproducible timings on a 2-socket host).  torchrun's OMP_NUM_THREADS=1 is overridden explicitly
-# through orc_set_num_threads.
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "threads")
+
+
+def _pin_openmp():
+    """The CPU arm's OpenMP runtime (the system libgomp the oracle links, a different instance from torch's bundled
+    one) reads these when the oracle library is first loaded: one thread per hardware thread, bound in place --
+    reproducible timings on a 2-socket host.  Set HERE, right before that load, and not at import: with OMP_PROC_BIND in
+    the environment every OpenMP runtime binds the process's initial thread to the first place when it initialises,
+    so setting it before `import torch` pins the main thread of EVERY torchrun rank to CPU 0 and the ranks time-slice
+    one core (measured: +10 ms per host-synchronised decode step at TP2).  torchrun's OMP_NUM_THREADS=1 is overridden
+    explicitly through orc_set_num_threads."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "threads")
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -166,6 +174,7 @@ def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
     is set explicitly and read back.  `repeats` timed runs of n steps each -> (median tok/s, runs, n, threads)."""
     from pegainfer_b200.synthetic import synthetic_prompt
     threads = host_threads()
+    _pin_openmp()
     O, orc = make_oracle(cfg, weights_np, num_pages=(ctx + 64) // 16 + 8)
     threads = O.set_num_threads(threads)
     orc.rehome_weights()
@@ -370,8 +379,12 @@ def run_ours(args, cfg, rank, world, dist):
             dist.barrier()
 
     # ---- parity of the model being benchmarked (before any timing) ----
-    parity = parity_check(model, cfg, prompt_len, world, rank, dist)
-    parity1 = parity_check(model, cfg, 128, 1, rank, dist) if world == 1 else None
+    if on_gpu:
+        parity = {"checked": False, "why": "--weights cuda: tuning checkpoint, not the fixtures' (use the default CPU checkpoint)"}
+        parity1 = None
+    else:
+        parity = parity_check(model, cfg, prompt_len, world, rank, dist)
+        parity1 = parity_check(model, cfg, 128, 1, rank, dist) if world == 1 else None
     # ---- warm-up: graph capture, allocator, clocks ----
     model.generate(prompt, 4)
     # ---- TTFT: prompt submit -> first token (host ids in, token out), median of 3 ----

@@ -25,6 +25,10 @@ struct ThreadState {
   size_t scratch_bytes = 0;
   int sm_count = 0;
   int device = -1;
+  // split-K workspace of the skinny tensor-core GEMM (gemm.cu): fp32 partial tiles + per-tile tickets
+  float* gemm_part = nullptr;
+  unsigned int* gemm_cnt = nullptr;
+  size_t gemm_part_bytes = 0;
 };
 ThreadState& tls();
 int sm_count();

@@ -83,7 +83,13 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                bf16* __restrict__ Y, bf16* __restrict__ Y1, bf16* __restrict__ Y2, int e0, int e1,
-               int M /*features*/, int N /*tokens*/, int K) {
+               int M /*features*/, int N /*tokens*/, int K, int splits, float* __restrict__ part,
+               unsigned int* __restrict__ cnt) {
+  // splits > 1 (skinny problems: one 128-token tile, few feature tiles, deep K -- prefill of a short prompt, decode
+  // buckets 5..64): the grid is tiles x splits CTAs, all co-resident; CTA (tile, sp) accumulates K blocks
+  // [sp * kb / splits, (sp + 1) * kb / splits), parks its fp32 partial in `part` ([work][feature][token]: coalesced
+  // both ways), and after the tile's `splits` partials have landed (ticket in cnt[2 * tile]) reduces ITS slice of the
+  // tile's features in split order -- a fixed summation order, so the result is deterministic -- and stores bf16.
   // Output features [0,e0) go to Y (row length e0), [e0,e1) to Y1, [e1,M) to Y2: the fused q|k|v
   // projection writes three HiddenStates buffers from one launch (e0 == e1 == M: plain GEMM).
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -99,8 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (N + BM - 1) / BM, n_tiles = (M + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles * splits;  // work items (tile, split)
+  const int k_blocks_all = (K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -125,9 +131,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int tile = work / splits, sp = work - tile * splits;
         const int mb = tile % m_tiles, nb = tile / m_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int kb0 = (int)(((int64_t)sp * k_blocks_all) / splits), kb1 = (int)(((int64_t)(sp + 1) * k_blocks_all) / splits);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty + s, (uint32_t)(((it / STAGES) & 1) ^ 1));
           mbar_expect_tx(full + s, STAGE_BYTES);
@@ -143,7 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(BM >> 4) << 24);
     int it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++lt) {
+      const int sp = work % splits;
+      const int kb0 = (int)(((int64_t)sp * k_blocks_all) / splits), kb1 = (int)(((int64_t)(sp + 1) * k_blocks_all) / splits);
+      const int k_blocks = kb1 - kb0;
       const int as = lt & 1;
       mbar_wait(tempty + as, (uint32_t)(((lt >> 1) & 1) ^ 1));
       tc_fence_after();
@@ -173,13 +184,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool vec_ok = (e0 % 32 == 0) && (e1 % 32 == 0) && (M % 8 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(Y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Y2) & 15) == 0);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++lt) {
+      const int tile = work / splits, sp = work - tile * splits;
       const int mb = tile % m_tiles, nb = tile / m_tiles;
       const int as = lt & 1;
       mbar_wait(tfull + as, (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const int tok = mb * BM + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (splits > 1) {
+        // ---- park the fp32 partial: part[work][feature][token] (a warp's 32 tokens are 128 contiguous bytes) ----
+        float* mine = part + (size_t)work * BN * BM;
+        const int trow = q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mine[(size_t)(c + j) * BM + trow] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + as);
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+        if (warp == 2 && lane == 0) {
+          atomicAdd(cnt + 2 * tile, 1u);
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile unsigned int*>(cnt + 2 * tile) < (unsigned)splits)
+            if (++spins > (1u << 26)) __trap();
+          __threadfence();
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        // ---- reduce this CTA's slice of the tile's features (8-feature groups dealt round-robin to the splits) ----
+        const float* base = part + (size_t)tile * splits * BN * BM;
+        for (int g8 = sp; g8 < BN / 8; g8 += splits) {
+          const int f0 = nb * BN + g8 * 8;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int s2 = 0; s2 < splits; ++s2) {
+            const float* src = base + ((size_t)s2 * BN + g8 * 8) * BM + trow;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += __ldcg(src + (size_t)j * BM);
+          }
+          if (tok < N && f0 < M) {
+            for (int j = 0; j < 8 && f0 + j < M; ++j) {
+              const int f = f0 + j;
+              bf16* d1 = f < e0 ? Y + (size_t)tok * e0 + f
+                                : (f < e1 ? Y1 + (size_t)tok * (e1 - e0) + (f - e0) : Y2 + (size_t)tok * (M - e1) + (f - e1));
+              *d1 = f2bf(acc[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          __threadfence();
+          if (atomicAdd(cnt + 2 * tile + 1, 1u) == (unsigned)splits - 1) {  // last reader: reset for the next launch / replay
+            cnt[2 * tile] = 0;
+            cnt[2 * tile + 1] = 0;
+            __threadfence();
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
@@ -237,6 +305,15 @@ static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int bo
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool gemm_splitk_enabled() {  // PK_GEMM_SPLITK=0: A/B switch
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_SPLITK");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BN, int STAGES>
 static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16* Y, bf16* Y1, bf16* Y2, int e0,
                              int e1, int M, int N, int K, cudaStream_t stream) {
@@ -249,7 +326,21 @@ static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, bf16*
   }
   const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
   int grid = tiles < sm_count() ? tiles : sm_count();
-  return launch(kern, dim3(grid), dim3(kGemmThreads), smem, stream, true, mx, mw, Y, Y1, Y2, e0, e1, M, N, K);
+  // Skinny problem (few tiles, deep K): split K across otherwise idle SMs.  Every (tile, split) CTA must be resident at
+  // once (they wait for each other's partials): grid = tiles * splits <= #SMs, one CTA per SM by shared-memory size.
+  ThreadState& ts = tls();
+  const int k_blocks = (K + BK - 1) / BK;
+  int splits = 1;
+  if (gemm_splitk_enabled() && ts.gemm_part && tiles * 2 <= sm_count() && tiles <= 1024) {
+    splits = sm_count() / tiles;
+    if (splits > k_blocks / 4) splits = k_blocks / 4;  // >= 4 K blocks (256 elements) per split
+    if (splits > BN / 8) splits = BN / 8;
+    while (splits > 1 && (size_t)tiles * splits * BM * BN * 4 > ts.gemm_part_bytes) --splits;
+    if (splits < 2) splits = 1;
+  }
+  if (splits > 1) grid = tiles * splits;
+  return launch(kern, dim3(grid), dim3(kGemmThreads), smem, stream, true, mx, mw, Y, Y1, Y2, e0, e1, M, N, K, splits,
+                ts.gemm_part, ts.gemm_cnt);
 }
 
 static int gemm_impl_mode() {  // 0 tcgen05 (default), 1 simt

@@ -158,8 +158,8 @@ gemv_stream_kernel(const GemvArgs a) {
         const int slot = (int)(seq & 1u);
         if (tid < a.tp.world) {
           const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas) * kTpMaxWorld + tid;
-          while (ld_acquire_sys(f) != seq) {
-          }
+          for (uint32_t spins = 0; ld_acquire_sys(f) != seq; ++spins)
+            if (spins > (1u << 27)) __trap();
         }
         consumer_bar();
         stage_base = a.tp.stage[a.tp.rank] + (size_t)slot * a.tp.world * a.tp.slot_bytes;

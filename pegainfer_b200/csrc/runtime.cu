@@ -43,6 +43,20 @@ void cublas_init() {
       ts.scratch_bytes = 0;
     }
   }
+  if (ts.gemm_part == nullptr) {  // split-K partial tiles: up to one 128 x 256 fp32 tile per SM, + tickets
+    const size_t bytes = (size_t)160 * 128 * 256 * 4;
+    void* p = nullptr;
+    void* c = nullptr;
+    if (cudaMalloc(&p, bytes) == cudaSuccess && cudaMalloc(&c, 4096) == cudaSuccess) {
+      cudaMemset(c, 0, 4096);
+      ts.gemm_part = static_cast<float*>(p);
+      ts.gemm_cnt = static_cast<unsigned int*>(c);
+      ts.gemm_part_bytes = bytes;
+    } else {
+      if (p) cudaFree(p);
+      cudaGetLastError();
+    }
+  }
   (void)pk::sm_count();
 }
 
@@ -52,6 +66,13 @@ void cublas_destroy() {
     cudaFree(ts.scratch);
     ts.scratch = nullptr;
     ts.scratch_bytes = 0;
+  }
+  if (ts.gemm_part != nullptr) {
+    cudaFree(ts.gemm_part);
+    cudaFree(ts.gemm_cnt);
+    ts.gemm_part = nullptr;
+    ts.gemm_cnt = nullptr;
+    ts.gemm_part_bytes = 0;
   }
 }
 

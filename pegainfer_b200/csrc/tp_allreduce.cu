@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
       const int p = threadIdx.x;
       st_release_sys(a.d.flags[p] + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + me, seq);
       const uint32_t* f = my_flags + (size_t)(slot * kTpMaxCtas + c) * kTpMaxWorld + p;
-      while (ld_acquire_sys(f) != seq) {
-      }
+      for (uint32_t spins = 0; ld_acquire_sys(f) != seq; ++spins)
+        if (spins > (1u << 27)) __trap();  // a lost peer becomes a launch failure instead of a wedged GPU
     }
     __syncthreads();
   }
@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
         } else if (LL) {
           const uint8_t* line = local + (size_t)r * a.d.slot_bytes + a.d.ll_off + ((size_t)t * nv + i) * 32;
           uint4 l0, l1;
-          do { l0 = ld_volatile_v4(line); } while (l0.y != seq || l0.w != seq);
-          do { l1 = ld_volatile_v4(line + 16); } while (l1.y != seq || l1.w != seq);
+          uint32_t spins = 0;
+          do { l0 = ld_volatile_v4(line); if (++spins > (1u << 27)) __trap(); } while (l0.y != seq || l0.w != seq);
+          do { l1 = ld_volatile_v4(line + 16); if (++spins > (1u << 27)) __trap(); } while (l1.y != seq || l1.w != seq);
           v = make_uint4(l0.x, l0.z, l1.x, l1.z);
         } else {
           v = __ldcg(reinterpret_cast<const uint4*>(local + (size_t)r * a.d.slot_bytes +

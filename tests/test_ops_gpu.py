@@ -224,13 +224,20 @@ def test_gemm_swiglu_epilogue(inter, N, K):
     assert lib.pk_b200_gemm_swiglu(p(dev(W)), p(dev(X)), p(act), inter, 64, K, stream()) == -2
 
 
-def test_gemm_graphsafe_batch_bucket(lib):  # decode bucket > 4 goes to the tensor-core path
-    M, N, K = 2560, 8, 2560
+@pytest.mark.parametrize("M,N,K", [(2560, 8, 2560), (2560, 64, 9728), (1024, 33, 2560)])
+def test_gemm_graphsafe_batch_bucket(lib, M, N, K):  # decode bucket > 4 goes to the tensor-core path (split-K when skinny)
     W, X = rnd((M, K), 19, 0.02), rnd((N, K), 20, 1.0)
+    W_d, X_d = dev(W), dev(X)
     Y = torch.zeros((N, M), dtype=torch.bfloat16, device="cuda")
-    lib.gemm_graphsafe_cuda(p(dev(W)), p(dev(X)), p(Y), M, N, K, stream())
+    lib.gemm_graphsafe_cuda(p(W_d), p(X_d), p(Y), M, N, K, stream())
     want = O.gemm(bits(W), bits(X))
     assert_bf16_close(bits(Y), want, 1, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.9)
+    # the split-K reduction sums the partial tiles in a fixed order: repeated launches are bit-identical
+    Y2 = torch.zeros_like(Y)
+    for _ in range(3):
+        lib.gemm_graphsafe_cuda(p(W_d), p(X_d), p(Y2), M, N, K, stream())
+    torch.cuda.synchronize()
+    assert (bits(Y2) == bits(Y)).all()
 
 
 # ------------------------------------------------------------------ QK norm + RoPE

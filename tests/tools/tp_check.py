@@ -78,6 +78,8 @@ def main():
             torch.cuda.synchronize()
             same = bool((y.view(torch.int16) == want.view(torch.int16)).all())
             ok &= rc == 0 and same
+            if not (rc == 0 and same):
+                print(f"[rank {rank}] all_reduce T={T} rep={rep}: rc={rc} same={same}", flush=True)
             if rank == 0 and not same:
                 print(f"all_reduce T={T} rep={rep}: MISMATCH max|d|={(y.float() - want.float()).abs().max().item()}")
     # ---- (1b) fused all-reduce + residual add + RMSNorm vs the oracle ----
@@ -100,11 +102,13 @@ def main():
         e_h = bool((bits(h_d) == h_np).all())
         err = np.abs(O.bf16_to_f32(bits(out)) - O.bf16_to_f32(want)) / O.bf16_ulp(np.abs(O.bf16_to_f32(want)))
         ok &= rc == 0 and e_h and err.max() <= 1
+        if not (rc == 0 and e_h and err.max() <= 1):
+            print(f"[rank {rank}] fused allreduce+add+norm T={T}: rc={rc} hidden exact={e_h} err={err.max():.2f}", flush=True)
         if rank == 0:
             print(f"fused allreduce+add+norm T={T}: hidden exact={e_h} max out err={err.max():.2f} ulp")
     # ---- (2) model parity: TP-N on GPUs vs TP-N oracle ----
     cfg = PRESETS[args.model]
-    tol = args.tol if args.tol is not None else (6 if cfg.num_hidden_layers <= 4 else 8)
+    tol = args.tol if args.tol is not None else (6 if cfg.num_hidden_layers <= 4 else 12)  # tests/test_fullsize_gpu.py TOL_ULP
     n_steps = args.steps
     prompt = [t % cfg.vocab_size for t in synthetic_prompt(args.prompt)]
     pages = (args.prompt + n_steps) // 16 + 4
@@ -130,7 +134,11 @@ def main():
         lg, sampled = m.decode([int(toks[i])], [kv])
         full = m.gather_logits(lg, dist)
         # the vocab-sharded greedy token (max/index exchange) must be the arg-max of the gathered row, lowest index on ties
-        ok &= int(sampled[0]) == int(full[0].float().argmax())
+        row = full[0].float()
+        first_max = int((row == row.max()).nonzero()[0])
+        if int(sampled[0]) != first_max:
+            print(f"[rank {rank}] step {i}: sampled {int(sampled[0])} != first arg-max {first_max} (value {float(row.max())})", flush=True)
+        ok &= int(sampled[0]) == first_max
         got.append(bits(full[0]))
     if rank == 0:
         worst = 0.0
