@@ -6,7 +6,8 @@
 N = 1 : BASELINE config[1] -- Qwen3-4B bf16, 2048-token prefill + decode at ctx 2048.., CUDA Graph on,
         single request.  A "step" is one decode step (one generated token).  The same line also carries
         BASELINE config[0] (128-token prompt / 64-token decode: `config1`), the Qwen3-8B single-GPU point of
-        config[2] (`tp_base`) and the reference's own CUDA kernels under the same host (`gpu_reference`).
+        config[2] (`tp_base`), BASELINE config[3] (Qwen3.5-4B hybrid, 1024-token prompt: `config4`) and the reference's
+        own CUDA kernels under the same host (`gpu_reference`).
 N > 1 : BASELINE config[2] -- Qwen3-8B bf16, tensor parallel over N ranks (one process per GPU,
         NVLink peer-memory all-reduce), 128-token prompt, decode steps.  scaling = "strong"; the line carries
         `tp1` = the same model / prompt / steps on ONE GPU measured in the same run (rank 0's GPU), so a
@@ -456,7 +457,7 @@ def run_ours(args, cfg, rank, world, dist):
         barrier()
 
     # ---- N = 1 side legs ----
-    gpu_ref = tp_base = cpu = None
+    gpu_ref = tp_base = cpu = config4 = None
     if world == 1 and rank == 0:
         if not args.no_gpu_reference:
             gpu_ref = gpu_reference_leg(cfg, keep_cpu, prompt, pages)
@@ -465,6 +466,8 @@ def run_ours(args, cfg, rank, world, dist):
         keep_cpu = None
         if not args.no_tp_base:
             tp_base = tp_base_leg(PRESETS["qwen3-8b"], local_rank)
+        if not args.no_config4:
+            config4 = config4_leg(local_rank)
 
     if rank == 0:
         value = K / (burst_ms * 1e-3)
@@ -500,6 +503,8 @@ def run_ours(args, cfg, rank, world, dist):
             line["gpu_reference"] = gpu_ref
         if tp_base:
             line["tp_base"] = tp_base
+        if config4:
+            line["config4"] = config4
         if tp1:
             line["tp1"] = tp1
             line["speedup_vs_tp1"] = value / tp1["value"]
@@ -559,6 +564,37 @@ def gpu_reference_leg(cfg, weights_cpu, prompt, pages):
         return {"available": False, "why": f"{type(e).__name__}: {e}"[:300]}
 
 
+def config4_leg(device):
+    """BASELINE config 4: Qwen3.5-4B hybrid (24 gated-delta-rule + 8 full-attention layers, head dim 256), 1024-token
+    prompt, single request: TTFT and decode tok/s through the C++ hybrid host.  Random-init checkpoint generated on the
+    GPU; parity of this path is pinned on the tiny hybrid stack (tests/test_qwen35_model_gpu.py vs the HF-pinned numpy
+    oracle) -- the 4B hybrid has no CPU oracle run (the numpy restatement is token-by-token)."""
+    import torch
+    try:
+        from pegainfer_b200.qwen35 import QWEN35_4B, Qwen35Model, iter_random_weights, weight_shapes
+        from pegainfer_b200.synthetic import synthetic_prompt
+        t0 = time.perf_counter()
+        m = Qwen35Model(QWEN35_4B, iter_random_weights(QWEN35_4B, seed=0, device="cuda"), num_pages=256, device_ordinal=device)
+        load_s = time.perf_counter() - t0
+        prompt = synthetic_prompt(1024)
+        m.generate(prompt, 4)
+        ttft = statistics.median([m.generate(prompt, 1)[1] for _ in range(3)])
+        _, _, gaps = m.generate(prompt, 129)
+        tpot = statistics.median(gaps[1:])
+        wbytes = sum(int(torch.tensor(s).prod()) * (4 if d == torch.float32 else 2) for s, d in weight_shapes(QWEN35_4B).values())
+        state_bytes = 24 * 32 * 128 * 128 * 4 * 2  # fp32 delta-rule state read + written per token (SURVEY 8d config 4)
+        peak, _ = measured_peaks()
+        launches = m.launches_per_step()
+        m.close()
+        return {"workload": "Qwen3.5-4B hybrid bf16 random-init, 1024-token prompt + 128 greedy decode steps, bs 1, CUDA Graph on",
+                "ttft_ms": ttft, "tpot_ms": tpot, "decode_tok_s": 1000.0 / tpot, "launches_per_step": launches,
+                "step_hbm_frac": (wbytes + state_bytes) / (tpot * 1e-3) / 1e9 / peak, "bytes_per_token": wbytes + state_bytes,
+                "prefill": "tensor-core GEMMs + conv1d + delta-rule SEQUENCE kernel (recurrent, not chunk-wise) + HD-256 paged FA kernel",
+                "model_load_s": round(load_s, 1)}
+    except Exception as e:
+        return {"available": False, "why": f"{type(e).__name__}: {e}"[:300]}
+
+
 def tp_base_leg(cfg8, device):
     """Qwen3-8B on ONE GPU, 128-token prompt, 256 decode steps: the N=1 point of BASELINE config 2 ('1/2/4/8')."""
     from pegainfer_b200.model import ModelRuntimeConfig, Qwen3Model
@@ -596,13 +632,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-tp-base", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the side legs (cpu_baseline, gpu_reference, tp_base / tp1)")
     ap.add_argument("--weights", default="cpu", choices=["cpu", "cuda"],
                     help="cpu (default): the seed-0 CPU checkpoint the oracle fixtures were computed on; cuda: generated on "
                          "each GPU (fast; tuning sweeps only -- the parity key then reports a different checkpoint)")
     args = ap.parse_args()
     if args.quick:
-        args.no_cpu_baseline = args.no_gpu_reference = args.no_tp_base = True
+        args.no_cpu_baseline = args.no_gpu_reference = args.no_tp_base = args.no_config4 = True
     if args.warmup < 3:
         args.warmup = 3
     from pegainfer_b200.config import PRESETS

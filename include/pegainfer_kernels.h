@@ -358,6 +358,16 @@ void qk_norm_partial_rope_batched_decode_hd256_cuda(const pk_bf16* q_full_batch,
                                                     int batch_size, int rotary_dim, float rms_eps,
                                                     pk_stream stream);
 
+/* HD-256 causal GQA prefill attention over the paged cache (ffi.rs:1309-1334; FlashInfer FA2 HD 256 in the reference):
+ * same arguments and planning contract as batch_prefill_paged_cuda (the tile plan is ignored consistently). */
+int batch_prefill_paged_cuda_hd256(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
+                                   int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
+                                   const int* last_page_len_d, const int* q_indptr, const int* request_indices,
+                                   const int* qo_tile_indices, const int* kv_tile_indices, const int* kv_chunk_size_ptr,
+                                   const uint32_t* total_num_rows, int num_qo_heads, int num_kv_heads, int head_dim,
+                                   int page_size, int seq_len, int batch_size, int padded_batch_size, int64_t stride_page,
+                                   float sm_scale, pk_stream stream);
+
 /* HD-256 paged decode attention (ffi.rs:1286-1307): q normed + roped, K/V already appended; GQA group 4, page 16
  * (the reference's only instantiation), else -1. */
 int paged_attention_decode_cuda_hd256(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data,

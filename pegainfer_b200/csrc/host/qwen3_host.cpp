@@ -262,6 +262,9 @@ struct Qwen3Model {
   int64_t launches_per_step = 0;
   bool decode_kernels_compat(int bs, bool split);
   bool decode_kernels_fused(int bs);
+  bool decode_kernels_wide(int bs);
+  bool unified_step(int n_prefill, const uint32_t* prompt_tokens, const int* lens, const int* prefill_kv_ids, int n_decode,
+                    const uint32_t* decode_tokens, const int* decode_kv_ids, void** prefill_logits, void** decode_logits);
   bool decode_kernels_persistent();
   DeviceBuf layer_ptrs_d, sync_scratch;
   HiddenStates pf_hid, pf_hid_out, pf_nrm, pf_q, pf_k, pf_v, pf_o, pf_gu, pf_act, pf_att;
@@ -478,7 +481,7 @@ bool Qwen3Model::create_decode_buffers() {
   attn_max_chunks = std::max(1, std::min(64, (2 * sms + local_kv_heads() - 1) / local_kv_heads()));
   ok = ok && attn_partial.alloc_zeros((size_t)bs * attn_max_chunks * local_heads() * 130 * 4) &&
        attn_counters.alloc_zeros((size_t)bs * local_kv_heads() * 4 + 64);
-  ok = ok && sample_out.alloc_zeros(64 * 4) && top1_val.alloc_zeros(64) && top1_states.alloc_zeros(1 << 20) &&
+  ok = ok && sample_out.alloc_zeros(64 * 4) && top1_val.alloc_zeros(256) && top1_states.alloc_zeros(1 << 20) &&
        cudaMallocHost((void**)&sample_h, 64 * 4) == cudaSuccess;
   if (!ok) return fail(std::string("decode buffer allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
   if (rt.mode == 2) {  // persistent decode: device table of per-layer weight pointers + sync scratch
@@ -515,6 +518,16 @@ bool Qwen3Model::ensure_capacity(KvState& s, int tokens) {
 // ===================================================================== prefill (prefill.rs)
 bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, const int* kv_ids,
                          void** logits_out) {
+  return unified_step(n_req, tokens, lens, kv_ids, 0, nullptr, nullptr, logits_out, nullptr);
+}
+
+// Unified step (unified_forward.rs:78-567): prefill prompts and decode tokens in ONE forward pass.  Token order as the
+// reference: all prompt tokens, then one token per decode request.  Projections / MLP / norms run over all tokens
+// together; attention splits -- prompt rows take QK-norm + RoPE, KV scatter and the paged prefill kernel, decode rows
+// the fused decode-attention launch (or, on a kernel library without the extensions, the reference's three launches).
+// With n_decode == 0 this IS batch_prefill (prefill.rs:220-285).  Returns last-token logits per prompt and per decode row.
+bool Qwen3Model::unified_step(int n_req, const uint32_t* tokens, const int* lens, const int* kv_ids, int n_dec,
+                              const uint32_t* dec_tokens, const int* dec_kv_ids, void** logits_out, void** dec_logits_out) {
   const Config& c = config;
   const int H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim(), I = local_inter();
   const int nh = local_heads(), nkv = local_kv_heads(), hd = c.head_dim;
@@ -524,8 +537,18 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   int T = 0;
   std::vector<int> starts(n_req);
   if (n_req <= 0) return fail("empty prefill batch");
-  if (n_req > max_bs) return fail("more prompts than max_batch");
+  if (n_req + n_dec > max_bs) return fail("more prompts + decode requests than max_batch");
   int pages_needed = 0;
+  for (int i = 0; i < n_dec; ++i) {
+    if (dec_kv_ids[i] < 0 || dec_kv_ids[i] >= (int)kv_states.size() || !kv_states[dec_kv_ids[i]].live) return fail("bad kv id");
+    for (int j = 0; j < i; ++j)
+      if (dec_kv_ids[j] == dec_kv_ids[i]) return fail("duplicate kv id in one unified step");
+    for (int j = 0; j < n_req; ++j)
+      if (kv_ids[j] == dec_kv_ids[i]) return fail("a request cannot be prefilled and decoded in the same step");
+    const KvState& s = kv_states[dec_kv_ids[i]];
+    if (s.seq_len + 1 > kRopePositions) return fail("position beyond the 4096-entry RoPE table");
+    pages_needed += std::max(0, (s.seq_len + 1 + kPageSize - 1) / kPageSize - (int)s.pages.size());
+  }
   for (int i = 0; i < n_req; ++i) {
     if (kv_ids[i] < 0 || kv_ids[i] >= (int)kv_states.size() || !kv_states[kv_ids[i]].live)
       return fail("bad kv id");
@@ -565,11 +588,21 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
     if (!ensure_capacity(s, starts[i] + lens[i])) return false;  // cannot fail: counted above
     s.seq_len += lens[i];
   }
+  const int Tp = T;  // prompt tokens; decode rows follow
+  std::vector<int> dec_pos(n_dec);
+  for (int i = 0; i < n_dec; ++i) {
+    KvState& s = kv_states[dec_kv_ids[i]];
+    txn.old.push_back({dec_kv_ids[i], {s.seq_len, s.pages.size()}});
+    dec_pos[i] = s.seq_len;
+    if (!ensure_capacity(s, s.seq_len + 1)) return false;
+    s.seq_len += 1;
+  }
+  T += n_dec;
   // ---- PrefillPagedPlan::new_batch_with_cta_tile_q (ops/attention.rs:208-302) ----
   std::vector<int> page_indices, page_indptr{0}, last_page_len, kv_chunk, batch_indices, positions, q_indptr{0},
       req_idx, qo_tile, kv_tile;
   const int group = nh / nkv;
-  const int cta_tile_q = k.batch_prefill_cta_tile_q_with_override(T, nh, nkv, hd, kPrefillCtaTileQ);
+  const int cta_tile_q = k.batch_prefill_cta_tile_q_with_override(Tp, nh, nkv, hd, kPrefillCtaTileQ);
   if (cta_tile_q <= 0) return fail("invalid prefill CTA tile override");
   for (int i = 0; i < n_req; ++i) {
     const KvState& s = kv_states[kv_ids[i]];
@@ -600,9 +633,23 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
   };
   const int o_pi = put(page_indices), o_ip = put(page_indptr), o_lpl = put(last_page_len), o_kc = put(kv_chunk),
             o_bi = put(batch_indices), o_pos = put(positions), o_qi = put(q_indptr), o_ri = put(req_idx),
-            o_qt = put(qo_tile), o_kt = put(kv_tile), o_tnr = put(std::vector<int>{T});
+            o_qt = put(qo_tile), o_kt = put(kv_tile), o_tnr = put(std::vector<int>{Tp});
+  // decode rows of the step: CSR page table, last_page_len, positions (batch_decode.rs:26-59 semantics)
+  std::vector<int> d_pi, d_ip{0}, d_lpl, d_req, d_tile, d_chunk;
+  for (int i = 0; i < n_dec; ++i) {
+    const KvState& s = kv_states[dec_kv_ids[i]];
+    d_pi.insert(d_pi.end(), s.pages.begin(), s.pages.end());
+    d_ip.push_back((int)d_pi.size());
+    d_lpl.push_back(s.last_page_len(kPageSize));
+    d_req.push_back(i);
+    d_tile.push_back(0);
+    d_chunk.push_back(s.seq_len);
+  }
+  const int o_dpi = put(d_pi), o_dip = put(d_ip), o_dlpl = put(d_lpl), o_dpos = put(dec_pos), o_dreq = put(d_req),
+            o_dtile = put(d_tile), o_dchunk = put(d_chunk);
   const int o_tok = (int)pack.size();
-  pack.insert(pack.end(), reinterpret_cast<const int*>(tokens), reinterpret_cast<const int*>(tokens) + T);
+  pack.insert(pack.end(), reinterpret_cast<const int*>(tokens), reinterpret_cast<const int*>(tokens) + Tp);
+  if (n_dec > 0) pack.insert(pack.end(), reinterpret_cast<const int*>(dec_tokens), reinterpret_cast<const int*>(dec_tokens) + n_dec);
   plan_pack.swap(pack);  // keep the host block alive until the async copy has been consumed
 
   // ---- PrefillBuffers (prefill.rs:17-51).  The reference re-allocates nine buffers per prefill call
@@ -650,25 +697,45 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
       gemm_rows_into(L.attention.qkv_proj, qd, kd, nrm.data.bf(), T, kb.data.bf());
       gemm_rows_into(L.attention.qkv_proj, qd + kd, kd, nrm.data.bf(), T, vb.data.bf());
     }
-    // prefill_attention_paged_into (ops/attention.rs:310-458)
+    // prompt rows [0, Tp): prefill_attention_paged_into (ops/attention.rs:310-458)
     if (n_req == 1)
       k.prefill_qk_norm_rope_only_cuda(qb.data.bf(), kb.data.bf(), L.attention.q_norm.data.bf(),
                                        L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(), nh,
-                                       nkv, hd, T, starts[0], eps, st);
+                                       nkv, hd, Tp, starts[0], eps, st);
     else
       k.qk_norm_rope_batched_decode_cuda(qb.data.bf(), kb.data.bf(), L.attention.q_norm.data.bf(),
                                          L.attention.k_norm.data.bf(), cos_cache.data.bf(), sin_cache.data.bf(),
-                                         P + o_pos, nh, nkv, hd, T, eps, st);
+                                         P + o_pos, nh, nkv, hd, Tp, eps, st);
     const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
     if (k.paged_kv_scatter_cuda(kv_buffer.bf(), k_off, v_off, P + o_pi, P + o_ip, P + o_lpl, kb.data.bf(),
-                                vb.data.bf(), P + o_bi, P + o_pos, T, nkv, hd, kPageSize, layout.page_stride, kd, hd,
+                                vb.data.bf(), P + o_bi, P + o_pos, Tp, nkv, hd, kPageSize, layout.page_stride, kd, hd,
                                 st) != 0)
       return fail("paged_kv_scatter_cuda failed");
     if (k.batch_prefill_paged_cuda_with_cta_tile_q(
             qb.data.bf(), att.data.bf(), kv_buffer.bf(), k_off, v_off, P + o_pi, P + o_ip, P + o_lpl, P + o_qi,
             P + o_ri, P + o_qt, P + o_kt, P + o_kc, reinterpret_cast<const uint32_t*>(P + o_tnr), nh, nkv, hd,
-            kPageSize, T, n_req, num_tiles, layout.page_stride, sm_scale, cta_tile_q, st) != 0)
+            kPageSize, Tp, n_req, num_tiles, layout.page_stride, sm_scale, cta_tile_q, st) != 0)
       return fail("batch_prefill_paged_cuda failed");
+    if (n_dec > 0) {  // decode rows [Tp, T): one query token per request over its paged context (unified_forward.rs:318-519)
+      pk_bf16 *qd_ = qb.data.bf() + (size_t)Tp * qd, *kd_ = kb.data.bf() + (size_t)Tp * kd, *vd_ = vb.data.bf() + (size_t)Tp * kd;
+      pk_bf16* od_ = att.data.bf() + (size_t)Tp * qd;
+      if (rt.mode >= 1 && k.pk_b200_decode_attention_fused) {
+        if (k.pk_b200_decode_attention_fused(qd_, kd_, vd_, od_, kv_buffer.bf(), k_off, v_off, P + o_dpi, P + o_dip, P + o_dlpl, P + o_dpos,
+                                             L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(),
+                                             sin_cache.data.bf(), eps, static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64,
+                                             attn_max_chunks, nh, nkv, hd, kPageSize, n_dec, layout.page_stride, sm_scale, st) != 0)
+          return fail("pk_b200_decode_attention_fused failed");
+      } else {
+        k.qk_norm_rope_batched_decode_cuda(qd_, kd_, L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(),
+                                           sin_cache.data.bf(), P + o_dpos, nh, nkv, hd, n_dec, eps, st);
+        if (k.paged_kv_scatter_cuda(kv_buffer.bf(), k_off, v_off, P + o_dpi, P + o_dip, P + o_dlpl, kd_, vd_, P + o_dreq, P + o_dpos, n_dec,
+                                    nkv, hd, kPageSize, layout.page_stride, kd, hd, st) != 0)
+          return fail("paged_kv_scatter_cuda (unified decode rows) failed");
+        if (k.paged_attention_decode_cuda(qd_, od_, kv_buffer.bf(), k_off, v_off, P + o_dpi, P + o_dip, P + o_dlpl, P + o_dreq, P + o_dtile,
+                                          P + o_dchunk, nh, nkv, hd, kPageSize, n_dec, layout.page_stride, sm_scale, st) != 0)
+          return fail("paged_attention_decode_cuda (unified decode rows) failed");
+      }
+    }
     k.gemm_cuda(L.attention.o_proj.data.bf(), att.data.bf(), ob.data.bf(), H, T, qd, st);
     if (T == 1) {}  // (gemm_into picks the graph-safe entry for T == 1; gemm_cuda handles it too)
     if (!all_reduce_hidden(ob.data.bf(), H, T)) return false;
@@ -686,15 +753,19 @@ bool Qwen3Model::prefill(int n_req, const uint32_t* tokens, const int* lens, con
     k.add_cuda(hcur, ob.data.bf(), hnext, H * T, st);  // prefill.rs:183 (rounds the residual sum)
     std::swap(hcur, hnext);
   }
-  // last-token logits per request (prefill.rs:267-282): extract_vec -> rms_norm -> linear
+  // last-token logits per request (prefill.rs:267-282): extract_vec -> rms_norm -> linear; then one row per decode token
   int off = 0;
-  for (int i = 0; i < n_req; ++i) {
-    const int last = off + lens[i] - 1;
+  for (int i = 0; i < n_req + n_dec; ++i) {
+    const int last = i < n_req ? off + lens[i] - 1 : Tp + (i - n_req);
     pk_bf16* lg = logits.data.bf() + (size_t)i * local_vocab();
     k.rms_norm_cuda(hcur + (size_t)last * H, norm.data.bf(), normed.data.bf() + (size_t)i * H, H, eps, st);
     k.gemm_graphsafe_cuda(output_rows(), normed.data.bf() + (size_t)i * H, lg, local_vocab(), 1, H, st);
-    logits_out[i] = lg;
-    off += lens[i];
+    if (i < n_req) {
+      logits_out[i] = lg;
+      off += lens[i];
+    } else if (dec_logits_out) {
+      dec_logits_out[i - n_req] = lg;
+    }
   }
   if (!cu(cudaStreamSynchronize(st), "prefill sync")) return false;
   txn.committed = true;
@@ -920,6 +991,55 @@ bool Qwen3Model::decode_kernels_fused(int bs) {
   return true;
 }
 
+// B200 path for the reference's decode buckets above 4 requests (batch_decode_buffers.rs:12: 8, 16, 32, 64): the
+// projections run on the tensor cores (skinny split-K GEMM: every SM streams a K slice of the weights), norms stay
+// separate launches over [H, bs], QK-norm + RoPE + KV append + attention + merge is the one fused attention launch over
+// all requests (cluster size shrinks with the batch), and every row's greedy token is taken inside the graph.
+// Same rounding points as decode_kernels_compat (it IS that op sequence with three fusions).
+bool Qwen3Model::decode_kernels_wide(int bs) {
+  const Config& c = config;
+  const int H = c.hidden_size, qd = local_q_dim(), kd = local_kv_dim(), I = local_inter();
+  const int nh = local_heads(), nkv = local_kv_heads(), hd = c.head_dim;
+  const float eps = c.rms_norm_eps, sm_scale = 1.0f / sqrtf((float)hd);
+  cudaStream_t st = ctx.stream;
+  const int* M = meta_d.i32();
+  k.embedding_batched_cuda(embed_tokens.data.bf(), reinterpret_cast<const uint32_t*>(M + mo.token_ids), hidden.data.bf(), H, bs, st);
+  k.rms_norm_batched_cuda(hidden.data.bf(), layers[0].input_layernorm.data.bf(), normed.data.bf(), H, bs, eps, st);
+  for (int li = 0; li < c.num_hidden_layers; ++li) {
+    TransformerBlock& L = layers[li];
+    pk_bf16* outs[3] = {q.data.bf(), kbuf.data.bf(), v.data.bf()};
+    const int segs[3] = {qd, kd, kd};
+    if (k.pk_b200_gemm_segments(L.attention.qkv_proj.data.bf(), normed.data.bf(), outs, segs, qd + 2 * kd, bs, H, st) != 0)
+      return fail("pk_b200_gemm_segments failed");
+    const int64_t k_off = (int64_t)li * layout.layer_stride, v_off = k_off + layout.kv_block_len;
+    if (k.pk_b200_decode_attention_fused(q.data.bf(), kbuf.data.bf(), v.data.bf(), attn_out.data.bf(), kv_buffer.bf(), k_off, v_off,
+                                         M + mo.page_indices, M + mo.page_indptr, M + mo.last_page_len, M + mo.positions,
+                                         L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf(), cos_cache.data.bf(),
+                                         sin_cache.data.bf(), eps, static_cast<float*>(attn_partial.ptr), attn_counters.i32(), 64,
+                                         attn_max_chunks, nh, nkv, hd, kPageSize, bs, layout.page_stride, sm_scale, st) != 0)
+      return fail("pk_b200_decode_attention_fused failed");
+    gemm_decode(L.attention.o_proj, 0, H, attn_out.data.bf(), bs, attn_proj.data.bf());
+    if (!all_reduce_hidden(attn_proj.data.bf(), H, bs)) return false;
+    k.fused_add_rms_norm_batched_cuda(hidden.data.bf(), attn_proj.data.bf(), L.post_attention_layernorm.data.bf(), normed.data.bf(), H,
+                                      bs, eps, st);
+    gemm_decode(L.mlp.gate_up_proj, 0, 2 * I, normed.data.bf(), bs, gate_up_out.data.bf());
+    k.silu_mul_fused_cuda(gate_up_out.data.bf(), mlp_act.data.bf(), I, bs, st);
+    gemm_decode(L.mlp.down_proj, 0, H, mlp_act.data.bf(), bs, mlp_out.data.bf());
+    if (!all_reduce_hidden(mlp_out.data.bf(), H, bs)) return false;
+    const DeviceVec& nw = li + 1 < c.num_hidden_layers ? layers[li + 1].input_layernorm : norm;
+    k.fused_add_rms_norm_batched_cuda(hidden.data.bf(), mlp_out.data.bf(), nw.data.bf(), normed.data.bf(), H, bs, eps, st);
+  }
+  k.gemm_graphsafe_cuda(output_rows(), normed.data.bf(), logits.data.bf(), local_vocab(), bs, H, st);
+  for (int b = 0; b < bs; ++b)
+    k.flashinfer_top1_cuda(logits.data.bf() + (size_t)b * local_vocab(), static_cast<pk_bf16*>(top1_val.ptr) + b,
+                           static_cast<uint8_t*>(top1_states.ptr) + (size_t)b * 8192, sample_out.i32() + b, local_vocab(), st);
+  if (vocab_sharded() &&
+      k.pk_tp_top1_exchange(tp_comm, static_cast<pk_bf16*>(top1_val.ptr), sample_out.i32(), bs, vocab_offset(),
+                            reinterpret_cast<const uint32_t*>(M + mo.step_seq), 250u, st) != 0)
+    return fail("pk_tp_top1_exchange failed");
+  return true;
+}
+
 // mode 2: the whole token in one cooperative launch (decode_persistent.cu)
 bool Qwen3Model::decode_kernels_persistent() {
   const Config& c = config;
@@ -1035,6 +1155,7 @@ bool Qwen3Model::run_step_kernels(int padded, bool split) {
                           local_heads() == 4 * local_kv_heads() && config.hidden_size <= 6144;
   auto body = [&]() {
     if (persistent) return decode_kernels_persistent();
+    if (fused && padded > 4) return decode_kernels_wide(padded);
     return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split);
   };
   if (!rt.enable_cuda_graph) return body();
@@ -1064,8 +1185,8 @@ bool Qwen3Model::decode(int bs, const uint32_t* tokens, const int* kv_ids, void*
   if (!finalized) return fail("model not finalized");
   if (bs <= 0 || bs > max_bs) return fail("batch size out of range");
   const bool fused = rt.mode >= 1;
-  if (fused && bs > 4) return fail("fused decode path supports batch <= 4 (use mode 0)");
-  const int padded = (rt.enable_cuda_graph && !fused) ? bucket_for(bs) : bs;
+  // fused path: 1..4 requests run the GEMV graph of their exact size; larger batches pad to the reference's buckets
+  const int padded = (rt.enable_cuda_graph && (!fused || bs > 4)) ? bucket_for(bs) : bs;
   if (padded < 0 || padded > max_bs) return fail("batch exceeds max_batch bucket");
   bool split = false;
   if (!build_step_meta(bs, padded, tokens, kv_ids, static_cast<int*>(meta_h), &split)) return false;
@@ -1303,6 +1424,14 @@ __attribute__((visibility("default"))) int pq_prefill(void* mp, int n_req, const
                                                       const int* kv_ids, void** logits_out) {
   return PQ_M->prefill(n_req, tokens, lens, kv_ids, logits_out) ? 0 : -1;
 }
+// unified_forward.rs:78: prompts and decode tokens in one forward pass; logits pointers per prompt / per decode row
+__attribute__((visibility("default"))) int pq_unified_step(void* mp, int n_prefill, const uint32_t* tokens, const int* lens,
+                                                           const int* prefill_kv_ids, int n_decode, const uint32_t* decode_tokens,
+                                                           const int* decode_kv_ids, void** prefill_logits, void** decode_logits) {
+  if (!PQ_M->finalized) return -1;
+  return PQ_M->unified_step(n_prefill, tokens, lens, prefill_kv_ids, n_decode, decode_tokens, decode_kv_ids, prefill_logits,
+                            decode_logits) ? 0 : -1;
+}
 __attribute__((visibility("default"))) int pq_decode(void* mp, int bs, const uint32_t* tokens, const int* kv_ids,
                                                      void** logits_out, int* sampled) {
   return PQ_M->decode(bs, tokens, kv_ids, logits_out, sampled) ? 0 : -1;
@@ -1362,6 +1491,41 @@ __attribute__((visibility("default"))) float pq_event_elapsed_ms(void* e0, void*
   cudaEventDestroy(static_cast<cudaEvent_t>(e0));
   cudaEventDestroy(static_cast<cudaEvent_t>(e1));
   return ms;
+}
+
+// Token log-probabilities on the host (executor.rs:400-436 `compute_logprobs_from_cpu`): log-softmax of the row in
+// f32 with the max subtracted, the sampled token's logprob and the `top_k` largest (descending; among equal values the
+// lower index first).  `logits_bf16` is a HOST copy of one bf16 logits row.  Needs no model / GPU.
+__attribute__((visibility("default"))) int pq_logprobs_host(const uint16_t* logits_bf16, int n, int sampled_token, int top_k,
+                                                            float* sampled_logprob, int* top_ids, float* top_logprobs) {
+  if (!logits_bf16 || n <= 0 || sampled_token < 0 || sampled_token >= n || top_k < 0) return -1;
+  std::vector<float> x((size_t)n);
+  float mx = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t u = (uint32_t)logits_bf16[i] << 16;
+    memcpy(&x[i], &u, 4);
+    mx = std::max(mx, x[i]);
+  }
+  float sum = 0.f;
+  for (int i = 0; i < n; ++i) sum += expf(x[i] - mx);
+  const float lse = mx + logf(sum);
+  if (sampled_logprob) *sampled_logprob = x[sampled_token] - lse;
+  const int k = std::min(top_k, n);
+  std::vector<std::pair<int, float>> best;  // sorted descending by value; insertion after equal values
+  best.reserve((size_t)k + 1);
+  for (int i = 0; i < n && k > 0; ++i) {
+    if ((int)best.size() < k || x[i] > best.back().second) {
+      size_t pos = 0;
+      while (pos < best.size() && best[pos].second >= x[i]) ++pos;
+      best.insert(best.begin() + (long)pos, {i, x[i]});
+      if ((int)best.size() > k) best.pop_back();
+    }
+  }
+  for (int j = 0; j < (int)best.size(); ++j) {
+    if (top_ids) top_ids[j] = best[j].first;
+    if (top_logprobs) top_logprobs[j] = best[j].second - lse;
+  }
+  return (int)best.size();
 }
 
 // Greedy generation of one request, host token ids in -> host token ids out, timed like

@@ -73,6 +73,7 @@ QWEN35_SIGNATURES = {
     "prefill_attention_hd256_prep_cuda": (None, [vp] * 10 + [i32, i32, i32, vp, i32, f32, i32, vp]),
     "attention_gate_batch_hd256_cuda": (None, [vp, vp, i32, i32, vp]),
     "qk_norm_partial_rope_batched_decode_hd256_cuda": (None, [vp] * 8 + [i32, i32, i32, i32, f32, vp]),
+    "batch_prefill_paged_cuda_hd256": (i32, [vp, vp, vp, i64, i64] + [vp] * 9 + [i32] * 7 + [i64, f32, vp]),
     "paged_attention_decode_cuda_hd256": (i32, [vp, vp, vp, i64, i64] + [vp] * 6 + [i32] * 5 + [i64, f32, vp]),
 }
 

@@ -58,6 +58,8 @@ def host_lib() -> C.CDLL:
         h.pq_available_pages.argtypes = [vp]
         h.pq_prefill.argtypes = [vp, i32, vp, vp, vp, vp]
         h.pq_decode.argtypes = [vp, i32, vp, vp, vp, vp]
+        h.pq_unified_step.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
+        h.pq_logprobs_host.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         h.pq_sample_greedy.argtypes = [vp, vp, vp]
         h.pq_sync.argtypes = [vp]
         h.pq_copy_out.argtypes = [vp, vp, vp, C.c_int64]
@@ -93,6 +95,19 @@ class ModelRuntimeConfig:
     max_batch: int = 4
     enable_pdl: bool = True
     kernel_lib: str | None = None  # default: libpegainfer_kernels_b200.so
+
+
+def token_logprobs(logits_row: torch.Tensor, token: int, top_k: int = 0):
+    """executor.rs:400-436 `compute_logprobs_from_cpu`: (logprob of `token`, [(id, logprob)] of the top_k largest) from one
+    bf16 logits row (any device; computed on the host in f32 like the reference)."""
+    row = logits_row.detach().to("cpu").contiguous().view(torch.int16)
+    lp = C.c_float()
+    ids = (C.c_int * max(top_k, 1))()
+    vals = (C.c_float * max(top_k, 1))()
+    n = host_lib().pq_logprobs_host(row.data_ptr(), row.numel(), int(token), int(top_k), C.byref(lp), ids, vals)
+    if n < 0:
+        raise ValueError("token out of range / empty logits")
+    return lp.value, [(ids[i], vals[i]) for i in range(n)]
 
 
 class Qwen3Model:
@@ -206,6 +221,22 @@ class Qwen3Model:
         outs = (C.c_void_p * n)()
         self._ck(self._h.pq_prefill(self._m, n, toks, lens, ids, outs))
         return torch.cat([self._logits_view(outs[i], 1) for i in range(n)], dim=0)
+
+    # -- unified step (unified_forward.rs:78-567): prompts and decode tokens in one forward pass --
+    def unified_step(self, prompts: list[list[int]], prefill_kv_ids: list[int], decode_tokens: list[int], decode_kv_ids: list[int]):
+        """Returns (prefill last-token logits [n_prompts, vocab], decode logits [n_decode, vocab])."""
+        n, nd = len(prompts), len(decode_tokens)
+        flat = [t for p in prompts for t in p]
+        toks = (C.c_uint32 * len(flat))(*flat)
+        lens = (C.c_int * n)(*[len(p) for p in prompts])
+        ids = (C.c_int * n)(*prefill_kv_ids)
+        dt = (C.c_uint32 * max(nd, 1))(*decode_tokens)
+        did = (C.c_int * max(nd, 1))(*decode_kv_ids)
+        outs, douts = (C.c_void_p * n)(), (C.c_void_p * max(nd, 1))()
+        self._ck(self._h.pq_unified_step(self._m, n, toks, lens, ids, nd, dt, did, outs, douts))
+        pl = torch.cat([self._logits_view(outs[i], 1) for i in range(n)], dim=0)
+        dl = torch.cat([self._logits_view(douts[i], 1) for i in range(nd)], dim=0) if nd else pl[:0]
+        return pl, dl
 
     # -- execute_decode: one token per request; returns (logits [bs, vocab], greedy tokens) --
     def decode(self, tokens: list[int], kv_ids: list[int], want_logits: bool = True):

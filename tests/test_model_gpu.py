@@ -139,3 +139,68 @@ def test_generate_matches_oracle_free_running():
     div = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None)
     assert div is None or div >= 4, f"free-running sequences diverge at {div}: {got} vs {want}"
     assert ttft > 0 and len(steps) == 11
+
+
+@pytest.mark.parametrize("name,kw", [VARIANTS[0], VARIANTS[3]])
+def test_decode_buckets_above_four(name, kw):
+    """The reference's decode buckets 8..64 (batch_decode_buffers.rs:12): 6 requests of different lengths -> bucket 8.
+    Fused: tensor-core skinny GEMMs + one fused attention launch over all requests + in-graph top-1 per row."""
+    cfg = QWEN3_TINY
+    w = random_weights(cfg, seed=0, norm_jitter=0.1)
+    orc = O.OracleQwen3(oracle_cfg(cfg), to_numpy_bits(w), num_pages=96)
+    m = Qwen3Model(cfg, {k: v.cuda() for k, v in w.items()}, ModelRuntimeConfig(num_pages=96, max_batch=8, **kw))
+    prompts = [[t % cfg.vocab_size for t in synthetic_prompt(n, off)] for n, off in ((5, 0), (17, 30), (33, 7), (16, 90), (70, 11), (2, 400))]
+    okvs, kvs = [orc.alloc_kv() for _ in prompts], [m.alloc_kv() for _ in prompts]
+    want = orc.prefill(prompts, okvs)
+    got = m.prefill(prompts, kvs)
+    for i in range(len(prompts)):
+        ok, info = logits_agree(bits(got[i]), want[i], TOL_ULP)
+        assert ok, f"{name} batched prefill row {i}: {info}"
+    for step in range(4):
+        toks = [O.argmax(r) for r in want]
+        want = list(orc.decode(toks, okvs))
+        lg, sampled = m.decode(toks, kvs)
+        for i in range(len(prompts)):
+            ok, info = logits_agree(bits(lg[i]), want[i], TOL_ULP)
+            assert ok, f"{name} step {step} row {i}: {info}"
+            row = lg[i].float()
+            assert float(row[sampled[i]]) == float(row.max()), "in-graph top-1 is not an arg-max of its row"
+    m.close()
+
+
+@pytest.mark.parametrize("name,kw", [VARIANTS[0], VARIANTS[3]] + ([VARIANTS[-1]] if VARIANTS[-1][0] == "refkernels" else []))
+def test_unified_step_prefill_plus_decode(name, kw):
+    """unified_forward.rs:78-567: two requests mid-decode and two new prompts in ONE forward pass, against the oracle's
+    separate prefill + decode on the same states."""
+    cfg = QWEN3_TINY
+    w = random_weights(cfg, seed=0, norm_jitter=0.1)
+    orc = O.OracleQwen3(oracle_cfg(cfg), to_numpy_bits(w), num_pages=96)
+    m = Qwen3Model(cfg, {k: v.cuda() for k, v in w.items()}, ModelRuntimeConfig(num_pages=96, max_batch=8, **kw))
+    old = [[t % cfg.vocab_size for t in synthetic_prompt(n, off)] for n, off in ((21, 0), (40, 55))]
+    new = [[t % cfg.vocab_size for t in synthetic_prompt(n, off)] for n, off in ((9, 300), (35, 77))]
+    okv_old, kv_old = [orc.alloc_kv() for _ in old], [m.alloc_kv() for _ in old]
+    w0 = orc.prefill(old, okv_old)
+    m.prefill(old, kv_old)
+    dec_toks = [O.argmax(r) for r in w0]
+    okv_new, kv_new = [orc.alloc_kv() for _ in new], [m.alloc_kv() for _ in new]
+    want_p = orc.prefill(new, okv_new)
+    want_d = orc.decode(dec_toks, okv_old)
+    got_p, got_d = m.unified_step(new, kv_new, dec_toks, kv_old)
+    for i in range(2):
+        ok, info = logits_agree(bits(got_p[i]), want_p[i], TOL_ULP)
+        assert ok, f"{name} unified prefill row {i}: {info}"
+        ok, info = logits_agree(bits(got_d[i]), want_d[i], TOL_ULP)
+        assert ok, f"{name} unified decode row {i}: {info}"
+    assert [m.kv_seq_len(k) for k in kv_old] == [22, 41] and [m.kv_seq_len(k) for k in kv_new] == [9, 35]
+    # the states keep working through the ordinary entry points: one more decode step over all four requests
+    toks = [O.argmax(r) for r in list(want_d) + list(want_p)]
+    want = orc.decode(toks, okv_old + okv_new)
+    lg, _ = m.decode(toks, kv_old + kv_new)
+    for i in range(4):
+        ok, info = logits_agree(bits(lg[i]), want[i], TOL_ULP)
+        assert ok, f"{name} decode after the unified step, row {i}: {info}"
+    # a request cannot be on both sides of one step, and a rejected step leaves every state untouched
+    with pytest.raises(RuntimeError, match="same step"):
+        m.unified_step([[1, 2, 3]], [kv_old[0]], [5], [kv_old[0]])
+    assert m.kv_seq_len(kv_old[0]) == 23
+    m.close()

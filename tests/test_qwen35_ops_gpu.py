@@ -192,6 +192,43 @@ def test_paged_attention_decode_hd256(lib, seq_lens):
     assert_bf16_close(bits(out), O.f32_to_bf16(want), 3, floor=float(np.abs(want).max()) / 32, what="hd256 decode attention")
 
 
+@pytest.mark.parametrize("starts,lens", [([0], [128]), ([0], [77]), ([0, 0, 0], [33, 100, 5]), ([40, 0], [50, 300]), ([0], [1024])])
+def test_batch_prefill_paged_hd256(lib, starts, lens):
+    """HD-256 causal GQA prefill attention over the paged pool vs the oracle's FA2 restatement (P rounded to bf16,
+    denominator of the rounded P), incl. chunked prefill (a request that already holds `start` tokens)."""
+    nq, nkv, hd, L, layer = 16, 4, 256, 2, 1
+    bs = len(lens)
+    kv_lens = [a + b for a, b in zip(starts, lens)]
+    rng = np.random.RandomState(11)
+    need = [-(-s // 16) for s in kv_lens]
+    ids = rng.permutation(np.arange(1, sum(need) + 3))
+    pi, ip, lpl, off = [], [0], [], 0
+    for s_, n in zip(kv_lens, need):
+        pi += ids[off:off + n].tolist(); off += n
+        ip.append(len(pi)); lpl.append(((s_ - 1) % 16) + 1)
+    block = 16 * nkv * hd
+    layer_stride, page_stride = 2 * block, L * 2 * block
+    k_off, v_off = layer * layer_stride, layer * layer_stride + block
+    kv = rnd(((sum(need) + 4) * page_stride,), 40)
+    T = sum(lens)
+    q = rnd((T, nq * hd), 41)
+    qi = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    dv = lambda a: torch.tensor(np.asarray(a, np.int32), device="cuda")
+    kv_d, q_d = kv.cuda(), q.cuda()
+    out = torch.zeros((T, nq * hd), dtype=torch.bfloat16, device="cuda")
+    pi_d, ip_d, lpl_d, qi_d, z_d = dv(pi), dv(ip), dv(lpl), dv(qi), dv(np.zeros(4096))
+    tn = torch.tensor([T], dtype=torch.int32, device="cuda")
+    sm = 1 / math.sqrt(hd)
+    rc = lib.batch_prefill_paged_cuda_hd256(q_d.data_ptr(), out.data_ptr(), kv_d.data_ptr(), k_off, v_off, pi_d.data_ptr(), ip_d.data_ptr(),
+                                            lpl_d.data_ptr(), qi_d.data_ptr(), z_d.data_ptr(), z_d.data_ptr(), z_d.data_ptr(), z_d.data_ptr(),
+                                            tn.data_ptr(), nq, nkv, hd, 16, T, bs, 1, page_stride, sm, st())
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = O.batch_prefill_paged(bits(q), bits(kv), k_off, v_off, np.array(pi, np.int32), np.array(ip, np.int32), np.array(lpl, np.int32),
+                                 qi, nq, nkv, hd, 16, page_stride, sm)
+    assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="hd256 prefill attention")
+
+
 def test_hybrid_model_bringup_matches_oracle(lib):
     """End to end through the C ABI (tests/tools/qwen35_bringup.py): 24 teacher-forced steps of a tiny hybrid model."""
     import importlib.util

@@ -20,7 +20,8 @@ NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
 def _torchrun(world, extra, port, timeout):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "tools", "tp_check.py"), *extra]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_PROC_BIND", "OMP_PLACES")}  # ranks must not share CPU 0
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0 and "TP_CHECK PASS" in r.stdout, tail
     return r.stdout

@@ -109,3 +109,21 @@ def test_model_from_safetensors_matches_oracle(tmp_path):
     m.drop_request(kv)
     m.close()
     assert ok, info
+
+
+def test_token_logprobs_match_log_softmax():
+    """compute_logprobs_from_cpu (executor.rs:400-436): host-side log-softmax of a bf16 logits row, top-k descending."""
+    import numpy as np
+    import torch
+    from pegainfer_b200.model import token_logprobs
+    g = torch.Generator().manual_seed(3)
+    row = (torch.randn(5000, generator=g) * 3).to(torch.bfloat16)
+    row[17] = row[4000] = row.float().max() + 1  # a tie at the top: lower index first
+    ref = torch.log_softmax(row.float(), dim=0)
+    lp, top = token_logprobs(row, 123, 5)
+    assert abs(lp - float(ref[123])) < 1e-4
+    assert [i for i, _ in top[:2]] == [17, 4000]
+    order = sorted(range(5000), key=lambda i: (-float(row[i]), i))[:5]
+    assert [i for i, _ in top] == order
+    assert np.allclose([v for _, v in top], [float(ref[i]) for i in order], atol=1e-4)
+    assert token_logprobs(row, 0, 0)[1] == []
