@@ -226,7 +226,9 @@ def test_batch_prefill_paged_hd256(lib, starts, lens):
     torch.cuda.synchronize()
     want = O.batch_prefill_paged(bits(q), bits(kv), k_off, v_off, np.array(pi, np.int32), np.array(ip, np.int32), np.array(lpl, np.int32),
                                  qi, nq, nkv, hd, 16, page_stride, sm)
-    assert_bf16_close(bits(out), want, 3, floor=float(np.abs(f32(want)).max()) / 32, what="hd256 prefill attention")
+    # FA2 rounds P against the RUNNING row max, the oracle against the final one (qwen3_oracle.c a8 note): with 256-long
+    # dot products and up to 1024 keys a few outputs land 4 ulp apart (measured worst 4.0 on B200)
+    assert_bf16_close(bits(out), want, 5, floor=float(np.abs(f32(want)).max()) / 32, what="hd256 prefill attention")
 
 
 def test_hybrid_model_bringup_matches_oracle(lib):
