@@ -201,6 +201,9 @@ int pk_b200_gemm_swiglu(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, i
  *             Y[0], the next seg_rows[1] -> Y[1], the rest -> Y[2] (the fused q|k|v projection).
  *   epi 1:    SwiGLU: W = [M gate rows | M up rows];
  *             Y[0][m] = bf16(silu(bf16(gate_m.x)) * bf16(up_m.x))  (csrc/fused_proj.cu:44-63).
+ *   x_mode 3: Qwen3.5 variant of x_mode 1: hidden_out = bf16(hidden + residual) and the norm runs on that ROUNDED sum with
+ *             (1 + w) weights (add_batch + rms_norm_batch_offset of pegainfer-qwen35-4b/src/batch_decode.rs:241-253).
+ *   epi 4:    like epi 1 with SiLU rounded to bf16 before the multiply (silu_mul_triton_aot_cuda, elementwise.cu:36-41).
  *   Tensor parallel, GEMV fused with its all-reduce over NVLink peer memory (no collective launch):
  *   epi 2:    the bf16 partial rows are pushed into every rank's staging slot and the grid's last CTA
  *             publishes the sequence flag (release.sys); Y is not written.

@@ -85,7 +85,8 @@ gemv_stream_kernel(const GemvArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
   const int M = a.M, K = a.K;
-  const int rows_per_group = a.epi == 1 ? kCW / 2 : kCW;
+  const bool glu = a.epi == 1 || a.epi == 4;  // interleaved gate / up row groups
+  const int rows_per_group = glu ? kCW / 2 : kCW;
   const int r0 = (int)(((int64_t)blockIdx.x * M) / G);
   const int r1 = (int)(((int64_t)(blockIdx.x + 1) * M) / G);
   const int groups = (r1 - r0 + rows_per_group - 1) / rows_per_group;
@@ -110,8 +111,8 @@ gemv_stream_kernel(const GemvArgs a) {
       // source row of consumer slot `lane` in this group (-1: none)
       int src = -1;
       if (lane < kCW) {
-        const int out_row = r0 + g * rows_per_group + (a.epi == 1 ? (lane & 3) : lane);
-        if (out_row < r1) src = a.epi == 1 ? (lane < 4 ? out_row : M + out_row) : out_row;
+        const int out_row = r0 + g * rows_per_group + (glu ? (lane & 3) : lane);
+        if (out_row < r1) src = glu ? (lane < 4 ? out_row : M + out_row) : out_row;
       }
       const unsigned valid = __ballot_sync(0xffffffffu, src >= 0);
       const int nvalid = __popc(valid);
@@ -192,6 +193,10 @@ gemv_stream_kernel(const GemvArgs a) {
             v[j][2] = bf16_lo(h.y) + bf16_lo(r.y); v[j][3] = bf16_hi(h.y) + bf16_hi(r.y);
             v[j][4] = bf16_lo(h.z) + bf16_lo(r.z); v[j][5] = bf16_hi(h.z) + bf16_hi(r.z);
             v[j][6] = bf16_lo(h.w) + bf16_lo(r.w); v[j][7] = bf16_hi(h.w) + bf16_hi(r.w);
+            if (a.x_mode == 3) {  // Qwen3.5: the residual sum is ROUNDED to bf16 before the norm (add_batch then norm)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j][e] = round_bf16(v[j][e]);
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
           }
@@ -210,11 +215,12 @@ gemv_stream_kernel(const GemvArgs a) {
           const int i = tid + j * kConsumerThreads;
           if (i < nv) {
             const uint4 g = g4[i];
+            const float wo = a.x_mode == 3 ? 1.0f : 0.0f;  // (1 + w) RMSNorm of Qwen3.5 (flashinfer_norm.cu:108-133)
             uint4 o;
-            o.x = pack_bf16(v[j][0] * rinv * bf16_lo(g.x), v[j][1] * rinv * bf16_hi(g.x));
-            o.y = pack_bf16(v[j][2] * rinv * bf16_lo(g.y), v[j][3] * rinv * bf16_hi(g.y));
-            o.z = pack_bf16(v[j][4] * rinv * bf16_lo(g.z), v[j][5] * rinv * bf16_hi(g.z));
-            o.w = pack_bf16(v[j][6] * rinv * bf16_lo(g.w), v[j][7] * rinv * bf16_hi(g.w));
+            o.x = pack_bf16(v[j][0] * rinv * (wo + bf16_lo(g.x)), v[j][1] * rinv * (wo + bf16_hi(g.x)));
+            o.y = pack_bf16(v[j][2] * rinv * (wo + bf16_lo(g.y)), v[j][3] * rinv * (wo + bf16_hi(g.y)));
+            o.z = pack_bf16(v[j][4] * rinv * (wo + bf16_lo(g.z)), v[j][5] * rinv * (wo + bf16_hi(g.z)));
+            o.w = pack_bf16(v[j][6] * rinv * (wo + bf16_lo(g.w)), v[j][7] * rinv * (wo + bf16_hi(g.w)));
             reinterpret_cast<uint4*>(xs + (size_t)n * K)[i] = o;
             if (blockIdx.x == 0) {
               uint4 hs;
@@ -235,7 +241,7 @@ gemv_stream_kernel(const GemvArgs a) {
   int s = 0;
   uint32_t ph = 0;
   for (int g = 0; g < groups; ++g) {
-    const int out_row = r0 + g * rows_per_group + (a.epi == 1 ? (warp & 3) : warp);
+    const int out_row = r0 + g * rows_per_group + (glu ? (warp & 3) : warp);
     const bool has_row = out_row < r1;
     float acc4[NTOK][4];
 #pragma unroll
@@ -285,7 +291,7 @@ gemv_stream_kernel(const GemvArgs a) {
     for (int n = 0; n < NTOK; ++n) acc[n] = (acc4[n][0] + acc4[n][1]) + (acc4[n][2] + acc4[n][3]);
 #pragma unroll
     for (int n = 0; n < NTOK; ++n) acc[n] = warp_sum(acc[n]);
-    if (a.epi >= 2) {
+    if (a.epi == 2 || a.epi == 3) {
       if (has_row && lane == 0) {
 #pragma unroll
         for (int n = 0; n < NTOK; ++n) ybuf[n * 64 + (out_row - r0)] = acc[n];
@@ -311,7 +317,9 @@ gemv_stream_kernel(const GemvArgs a) {
         for (int n = 0; n < NTOK; ++n) {
           const float gt = round_bf16(acc[n]);                   // gate_up_out is bf16 in the reference
           const float up = round_bf16(sw[warp * NTOK + n]);
-          a.Y[0][(size_t)n * M + out_row] = f2bf(gt / (1.0f + expf(-gt)) * up);
+          float sl = gt / (1.0f + expf(-gt));
+          if (a.epi == 4) sl = round_bf16(sl);                   // Qwen3.5's unfused silu_mul rounds SiLU first (elementwise.cu:36-41)
+          a.Y[0][(size_t)n * M + out_row] = f2bf(sl * up);
         }
       }
     }
@@ -454,7 +462,7 @@ bool gemv_stream_supported(const void* W, const void* X, int N, int K) {
 // CTA count of the streaming kernel: every CTA owns >= one row group, at most ctas_per_sm CTAs per SM.
 int gemv_grid(int M, int epi) {
   gemv_tuning();
-  const int rpg = epi == 1 ? kCW / 2 : kCW;
+  const int rpg = (epi == 1 || epi == 4) ? kCW / 2 : kCW;
   int grid = sm_count() * g_gemv_ctas_per_sm;
   const int max_useful = (M + rpg - 1) / rpg;
   if (grid > max_useful) grid = max_useful;
@@ -482,7 +490,7 @@ static cudaError_t launch_gemv_t(GemvArgs a, cudaStream_t stream) {
     configured[NTOK] = smem;
   }
   const int grid = gemv_grid(a.M, a.epi);
-  if (a.epi >= 2 && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
+  if ((a.epi == 2 || a.epi == 3) && (a.M + grid - 1) / grid > 64) return cudaErrorInvalidValue;
   return launch(kern, dim3(grid), dim3(kConsumerThreads + 32), smem, stream, true, a);
 }
 
@@ -549,6 +557,7 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* g, pk_stream stream) {
   if (!g || g->M <= 0 || g->K <= 0) return -1;
   if (!gemv_stream_supported(g->W, g->X, g->N, g->K)) return -1;
   if (g->x_mode >= 1 && (g->hidden_out == nullptr || g->hidden_out == g->X || g->K > 10240)) return -1;
+  if (g->x_mode < 0 || g->x_mode > 3 || g->epi < 0 || g->epi > 4) return -1;
   GemvArgs a{};
   a.W = (const bf16*)g->W;
   a.X = (const bf16*)g->X;

@@ -82,8 +82,8 @@ struct Layer {
   // full attention: stacked [q_proj (2 nq hd) ; k_proj ; v_proj], o_proj, norms
   Mat qkv, o;
   DeviceBuf q_norm, k_norm;        // [hd] bf16
-  // linear attention: stacked [in_proj_qkv ; in_proj_z ; in_proj_b], in_proj_a, conv, dt_bias, A_log (f32), norm (f32), out_proj
-  Mat in_qzb, in_a, conv_w, out_proj;
+  // linear attention: stacked in-projections, conv, dt_bias, A_log (f32), norm (f32), out_proj
+  Mat in_qzba, conv_w, out_proj;  // in_qzba = [in_proj_qkv ; in_proj_z ; in_proj_b ; in_proj_a]
   DeviceBuf dt_bias, A_log, gnorm;
   int loaded = 0;
 };
@@ -115,7 +115,7 @@ struct Model {
   bool finalized = false;
   // scratch (decode: 1 token; prefill: grown to T)
   int cap = 0;
-  DeviceBuf h, h2, x, big0, big1, big2, conv_o, heads, normed, attn_o, gate, up, act, mo, kc, vc, q_prep, a_seq;
+  DeviceBuf h, h2, x, big0, big1, big2, conv_o, heads, normed, attn_o, gate, up, act, mo, mo2, zero_res, kc, vc, q_prep, a_seq;
   DeviceBuf logits, meta_d, sample_out, top1_val, top1_states;
   int* meta_h = nullptr;
   int* sample_h = nullptr;
@@ -153,6 +153,9 @@ struct Model {
   bool layer_tail(Layer& L, int T, pk_bf16* hcur, pk_bf16* attn_out_proj, pk_bf16* hnext);
   bool prefill(int rid, const uint32_t* tokens, int n, void** logits_out);
   bool decode_body(Request& r);
+  bool decode_body_fused(Request& r);
+  bool gemv_f(const pk_bf16* W, const pk_bf16* X, int M, int K, pk_bf16* y0, pk_bf16* y1, pk_bf16* y2, int s0, int s1, int s2,
+              const pk_bf16* residual, const pk_bf16* norm_w, pk_bf16* hidden_out, int epi);
   bool decode(int rid, uint32_t token, void** logits_out, int* sampled);
   bool gemv(const pk_bf16* W, const pk_bf16* X, int M, int K, pk_bf16* y0, pk_bf16* y1, pk_bf16* y2, int s0, int s1, int s2);
 };
@@ -212,12 +215,13 @@ bool Model::load_tensor(const std::string& name, const void* data, int rows, int
     else if (L.full && sub == "self_attn.q_norm.weight") ok = want(1, hd, 0) && up_vec(L.q_norm, data, (size_t)hd * 2);
     else if (L.full && sub == "self_attn.k_norm.weight") ok = want(1, hd, 0) && up_vec(L.k_norm, data, (size_t)hd * 2);
     else if (!L.full && sub == "linear_attn.in_proj_qkv.weight")
-      ok = want(qkvd, H, 0) && alloc_mat(L.in_qzb, qkvd + zd + nv, H) && up_rows(L.in_qzb, 0, data, qkvd, H);
+      ok = want(qkvd, H, 0) && alloc_mat(L.in_qzba, qkvd + zd + 2 * nv, H) && up_rows(L.in_qzba, 0, data, qkvd, H);
     else if (!L.full && sub == "linear_attn.in_proj_z.weight")
-      ok = want(zd, H, 0) && alloc_mat(L.in_qzb, qkvd + zd + nv, H) && up_rows(L.in_qzb, qkvd, data, zd, H);
+      ok = want(zd, H, 0) && alloc_mat(L.in_qzba, qkvd + zd + 2 * nv, H) && up_rows(L.in_qzba, qkvd, data, zd, H);
     else if (!L.full && sub == "linear_attn.in_proj_b.weight")
-      ok = want(nv, H, 0) && alloc_mat(L.in_qzb, qkvd + zd + nv, H) && up_rows(L.in_qzb, qkvd + zd, data, nv, H);
-    else if (!L.full && sub == "linear_attn.in_proj_a.weight") ok = want(nv, H, 0) && alloc_mat(L.in_a, nv, H) && up_rows(L.in_a, 0, data, nv, H);
+      ok = want(nv, H, 0) && alloc_mat(L.in_qzba, qkvd + zd + 2 * nv, H) && up_rows(L.in_qzba, qkvd + zd, data, nv, H);
+    else if (!L.full && sub == "linear_attn.in_proj_a.weight")
+      ok = want(nv, H, 0) && alloc_mat(L.in_qzba, qkvd + zd + 2 * nv, H) && up_rows(L.in_qzba, qkvd + zd + nv, data, nv, H);
     else if (!L.full && sub == "linear_attn.conv1d.weight")
       ok = want(qkvd, c.linear_conv_kernel_dim, 0) && alloc_mat(L.conv_w, qkvd, c.linear_conv_kernel_dim) &&
            up_rows(L.conv_w, 0, data, qkvd, c.linear_conv_kernel_dim);
@@ -297,7 +301,8 @@ bool Model::ensure_scratch(int T) {
             big1.alloc_uninit(std::max<size_t>(z_dim(), kv_dim()) * n * 2) && big2.alloc_uninit(std::max<size_t>(kv_dim(), 64) * n * 2) &&
             conv_o.alloc_uninit((size_t)qkv_dim() * n * 2) && heads.alloc_uninit((size_t)z_dim() * n * 2) &&
             normed.alloc_uninit((size_t)z_dim() * n * 2) && attn_o.alloc_uninit((size_t)q_dim() * n * 2) && gate.alloc_uninit(I * n * 2) &&
-            up.alloc_uninit(I * n * 2) && act.alloc_uninit(I * n * 2) && mo.alloc_uninit(H * n * 2) && q_prep.alloc_uninit((size_t)q_dim() * n * 2) &&
+            up.alloc_uninit(I * n * 2) && act.alloc_uninit(I * n * 2) && mo.alloc_uninit(H * n * 2) && mo2.alloc_uninit(H * n * 2) &&
+            zero_res.alloc_zeros(H * 2) && q_prep.alloc_uninit((size_t)q_dim() * n * 2) &&
             a_seq.alloc_uninit((size_t)std::max(64, c.linear_num_value_heads) * n * 2);
   if (!ok) return fail("scratch allocation failed");
   cap = n;
@@ -430,12 +435,13 @@ bool Model::prefill(int rid, const uint32_t* tokens, int n, void** logits_out) {
       // gated delta rule over the sequence, gated RMSNorm, out_proj
       pk_bf16* outs[3] = {big0.bf(), big1.bf(), big2.bf()};
       const int segs[3] = {qkvd, zd, nv};
+      const pk_bf16* w_a = L.in_qzba.p() + (size_t)(qkvd + zd + nv) * H;  // the in_proj_a rows of the stacked matrix
       if (T == 1) {
-        gemv(L.in_qzb.p(), x.bf(), qkvd + zd + nv, H, outs[0], outs[1], outs[2], qkvd, zd, nv);
-        k.gemm_graphsafe_cuda(L.in_a.p(), x.bf(), a_seq.bf(), nv, 1, H, st);
+        gemv(L.in_qzba.p(), x.bf(), qkvd + zd + nv, H, outs[0], outs[1], outs[2], qkvd, zd, nv);
+        k.gemm_graphsafe_cuda(w_a, x.bf(), a_seq.bf(), nv, 1, H, st);
       } else {
-        if (k.pk_b200_gemm_segments(L.in_qzb.p(), x.bf(), outs, segs, qkvd + zd + nv, T, H, st) != 0) return fail("in_proj GEMM failed");
-        k.gemm_cuda(L.in_a.p(), x.bf(), a_seq.bf(), nv, T, H, st);
+        if (k.pk_b200_gemm_segments(L.in_qzba.p(), x.bf(), outs, segs, qkvd + zd + nv, T, H, st) != 0) return fail("in_proj GEMM failed");
+        k.gemm_cuda(w_a, x.bf(), a_seq.bf(), nv, T, H, st);
       }
       k.conv1d_prefill_cuda(big0.bf(), L.conv_w.p(), r.conv[lin].bf(), conv_o.bf(), qkvd, T, c.linear_conv_kernel_dim, st);
       if (k.pk_b200_gated_delta_rule_prefill_recurrent(conv_o.bf(), big2.bf(), a_seq.bf(), L.dt_bias.bf(), static_cast<const float*>(L.A_log.ptr),
@@ -487,8 +493,8 @@ bool Model::decode_body(Request& r) {
       k.gemm_graphsafe_cuda(L.o.p(), attn_o.bf(), mo.bf(), H, 1, q_dim(), st);
       ++fi;
     } else {
-      gemv(L.in_qzb.p(), x.bf(), qkvd + zd + nv, H, big0.bf(), big1.bf(), big2.bf(), qkvd, zd, nv);
-      k.gemm_graphsafe_cuda(L.in_a.p(), x.bf(), a_seq.bf(), nv, 1, H, st);
+      gemv(L.in_qzba.p(), x.bf(), qkvd + zd + nv, H, big0.bf(), big1.bf(), big2.bf(), qkvd, zd, nv);
+      k.gemm_graphsafe_cuda(L.in_qzba.p() + (size_t)(qkvd + zd + nv) * H, x.bf(), a_seq.bf(), nv, 1, H, st);
       k.conv1d_prefill_cuda(big0.bf(), L.conv_w.p(), r.conv[lin].bf(), conv_o.bf(), qkvd, 1, c.linear_conv_kernel_dim, st);
       k.gated_delta_rule_decode_cuda(conv_o.bf(), big2.bf(), a_seq.bf(), L.dt_bias.bf(), static_cast<const float*>(L.A_log.ptr),
                                      static_cast<float*>(r.S[lin].ptr), heads.bf(), nk, nv, dk, dv, st);
@@ -500,6 +506,71 @@ bool Model::decode_body(Request& r) {
   }
   k.rms_norm_offset_cuda(h.bf(), norm.bf(), x.bf(), H, eps, st);
   k.gemm_graphsafe_cuda(embed.p(), x.bf(), logits.bf(), c.vocab_size, 1, H, st);
+  k.flashinfer_top1_cuda(logits.bf(), static_cast<pk_bf16*>(top1_val.ptr), static_cast<uint8_t*>(top1_states.ptr), sample_out.i32(), c.vocab_size, st);
+  return true;
+}
+
+// GEMV with the Qwen3.5 prologue (x_mode 3: hidden_out = bf16(X + residual), x = (1 + w) RMSNorm of that rounded sum) and,
+// for epi 4, the rounded-SiLU SwiGLU epilogue
+bool Model::gemv_f(const pk_bf16* W, const pk_bf16* X, int M, int K, pk_bf16* y0, pk_bf16* y1, pk_bf16* y2, int s0, int s1, int s2,
+                   const pk_bf16* residual, const pk_bf16* norm_w, pk_bf16* hidden_out, int epi) {
+  pk_b200_gemv_args g{};
+  g.W = W; g.X = X;
+  g.Y[0] = y0; g.Y[1] = y1; g.Y[2] = y2;
+  g.seg_rows[0] = s0; g.seg_rows[1] = s1; g.seg_rows[2] = s2;
+  g.M = M; g.N = 1; g.K = K;
+  g.x_mode = 3; g.residual = residual; g.norm_w = norm_w; g.eps = c.rms_norm_eps; g.hidden_out = hidden_out; g.epi = epi;
+  if (k.pk_b200_gemv_fused(&g, st) != 0) return fail("pk_b200_gemv_fused rejected its arguments");
+  return true;
+}
+
+// Fused decode token (default): the two adds + two (1+w) norms of a layer ride in the prologues of the in-projection
+// and gate_up GEMVs, SiLU-mul in the gate_up epilogue, b and a come out of the in-projection launch: 8 launches per
+// layer instead of 14, same rounding points (PK_Q35_FUSED=0 keeps the launch-per-op sequence).
+bool Model::decode_body_fused(Request& r) {
+  const int H = c.hidden_size, I = c.intermediate_size, hd = c.head_dim, nq = c.num_attention_heads, nkv = c.num_key_value_heads;
+  const int nk = c.linear_num_key_heads, nv = c.linear_num_value_heads, dk = c.linear_key_head_dim, dv = c.linear_value_head_dim;
+  const int qf = 2 * q_dim(), kd = kv_dim(), qkvd = qkv_dim(), zd = z_dim();
+  const float eps = c.rms_norm_eps;
+  const int* M = meta_d.i32();
+  pk_bf16 *Ha = h.bf(), *Hb = h2.bf();
+  k.embedding_batched_cuda(embed.p(), reinterpret_cast<const uint32_t*>(M), Ha, H, 1, st);
+  const pk_bf16* prev = zero_res.bf();  // layer 0: hidden + 0
+  int fi = 0, lin = 0;
+  for (int li = 0; li < c.num_hidden_layers; ++li) {
+    Layer& L = layers[li];
+    if (L.full) {
+      // Hb = Ha + prev; q_full | k | v = W . norm(Hb)
+      if (!gemv_f(L.qkv.p(), Ha, qf + 2 * kd, H, big0.bf(), big1.bf(), big2.bf(), qf, kd, kd, prev, L.in_ln.bf(), Hb, 0)) return false;
+      k.qk_norm_partial_rope_batched_decode_hd256_cuda(big0.bf(), big1.bf(), L.q_norm.bf(), L.k_norm.bf(), cosc.bf(), sinc.bf(), M + 1, q_prep.bf(),
+                                                       nq, nkv, 1, c.rotary_dim, eps, st);
+      const int64_t k_off = (int64_t)fi * layer_stride, v_off = k_off + block;
+      if (k.paged_kv_scatter_cuda(kv.bf(), k_off, v_off, M + 6, M + 2, M + 4, big1.bf(), big2.bf(), M + 5, M + 1, 1, nkv, hd, kPage, page_stride,
+                                  (int64_t)nkv * hd, hd, st) != 0)
+        return fail("paged_kv_scatter_cuda failed");
+      if (k.paged_attention_decode_cuda_hd256(q_prep.bf(), attn_o.bf(), kv.bf(), k_off, v_off, M + 6, M + 2, M + 4, M + 5, M + 5, M + 5, nq, nkv, hd,
+                                              kPage, 1, page_stride, 1.0f / sqrtf((float)hd), st) != 0)
+        return fail("paged_attention_decode_cuda_hd256 failed");
+      k.attention_gate_batch_hd256_cuda(big0.bf(), attn_o.bf(), nq, 1, st);
+      k.gemm_graphsafe_cuda(L.o.p(), attn_o.bf(), mo.bf(), H, 1, q_dim(), st);
+      ++fi;
+    } else {
+      // Hb = Ha + prev; qkv | z | [b; a] = W . norm(Hb)
+      if (!gemv_f(L.in_qzba.p(), Ha, qkvd + zd + 2 * nv, H, big0.bf(), big1.bf(), big2.bf(), qkvd, zd, 2 * nv, prev, L.in_ln.bf(), Hb, 0)) return false;
+      k.conv1d_prefill_cuda(big0.bf(), L.conv_w.p(), r.conv[lin].bf(), conv_o.bf(), qkvd, 1, c.linear_conv_kernel_dim, st);
+      k.gated_delta_rule_decode_cuda(conv_o.bf(), big2.bf(), big2.bf() + nv, L.dt_bias.bf(), static_cast<const float*>(L.A_log.ptr),
+                                     static_cast<float*>(r.S[lin].ptr), heads.bf(), nk, nv, dk, dv, st);
+      k.rms_norm_gated_cuda(heads.bf(), static_cast<const float*>(L.gnorm.ptr), big1.bf(), normed.bf(), nv, dv, eps, st);
+      k.gemm_graphsafe_cuda(L.out_proj.p(), normed.bf(), mo.bf(), H, 1, zd, st);
+      ++lin;
+    }
+    // Ha = Hb + attn; act = bf16(bf16(silu(gate)) * up) with gate | up = W . norm(Ha)
+    if (!gemv_f(L.gate_up.p(), Hb, I, H, act.bf(), nullptr, nullptr, I, 0, 0, mo.bf(), L.post_ln.bf(), Ha, 4)) return false;
+    k.gemm_graphsafe_cuda(L.down.p(), act.bf(), mo2.bf(), H, 1, I, st);
+    prev = mo2.bf();
+  }
+  // logits = embed . norm(Ha + mlp)
+  if (!gemv_f(embed.p(), Ha, c.vocab_size, H, logits.bf(), nullptr, nullptr, c.vocab_size, 0, 0, prev, norm.bf(), Hb, 0)) return false;
   k.flashinfer_top1_cuda(logits.bf(), static_cast<pk_bf16*>(top1_val.ptr), static_cast<uint8_t*>(top1_states.ptr), sample_out.i32(), c.vocab_size, st);
   return true;
 }
@@ -520,14 +591,17 @@ bool Model::decode(int rid, uint32_t token, void** logits_out, int* sampled) {
   meta_h[5] = 0;
   memcpy(meta_h + 6, r.pages.data(), r.pages.size() * 4);
   if (!cu(cudaMemcpyAsync(meta_d.ptr, meta_h, (size_t)meta_ints * 4, cudaMemcpyHostToDevice, st), "meta H2D")) return false;
+  const char* fe = getenv("PK_Q35_FUSED");  // read per call: the tests flip it between models
+  const bool fused = !(fe && atoi(fe) == 0);
+  auto body = [&]() { return fused ? decode_body_fused(r) : decode_body(r); };
   if (!use_graph) {
-    if (!decode_body(r)) return false;
+    if (!body()) return false;
   } else {
     cudaGraphExec_t& g = graphs[rid];  // the graph bakes this request's recurrent-state pointers
     if (!g) {
       const int64_t before = k.pk_b200_launch_count(0);
       if (!cu(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return false;
-      const bool ok = decode_body(r);
+      const bool ok = body();
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (!ok) {

@@ -6,6 +6,8 @@
 // cited per function; oracle/qwen35_oracle.py restates them and is pinned to HF.
 // STATUS: compiled for sm_100a and exported; the GPU parity tests (tests/test_qwen35_ops_gpu.py) are opt-in
 // (PK_TEST_QWEN35=1) until they have run on hardware.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pk {
@@ -208,6 +210,94 @@ gated_delta_rule_seq_kernel(const bf16* __restrict__ qkv_seq, const bf16* __rest
   for (int j = 0; j < GJ; ++j) st[(size_t)j * GV] = s[j];
 }
 
+// ---------------------------------------------------------------- delta rule over a sequence, version 2 (round 2)
+// The per-token critical path of gated_delta_rule_seq_kernel is six block barriers (two norm reductions among them) on a
+// 512-thread CTA, and only 32 CTAs exist (one per value head): 61 ms TTFT at 1024 tokens, ~60 % of it here.  Everything
+// that does not depend on the state -- the L2 norms of q and k, the q scale, decay = exp(-exp(A_log) softplus(a + dt_bias))
+// and beta = sigmoid(b) -- is hoisted into a token-parallel pre-pass (fp32, same formulas); the sequential kernel then
+// needs TWO barriers per token (the two 4-way partial sums), runs 4 CTAs per value head (32 state columns each, 128
+// threads: cheaper barriers, 128 CTAs) and stages the next token's rows while the current one is reduced.
+__global__ void __launch_bounds__(GK) gdr_prepare_kernel(const bf16* __restrict__ qkv_seq, const bf16* __restrict__ b_seq,
+                                                         const bf16* __restrict__ a_seq, const bf16* __restrict__ dt_bias,
+                                                         const float* __restrict__ a_log, float* __restrict__ qn, float* __restrict__ kn,
+                                                         float* __restrict__ decay, float* __restrict__ beta, int nk, int nv, int T) {
+  __shared__ float red[40];
+  pdl_wait();
+  const int t = blockIdx.x, kh = blockIdx.y, d = threadIdx.x;
+  const int qkv_dim = 2 * nk * GK + nv * GV;
+  if (kh == nk) {  // one extra block row: the per-(token, value head) scalars
+    for (int vh = d; vh < nv; vh += GK) {
+      const float x = bf2f(a_seq[(size_t)t * nv + vh]) + bf2f(dt_bias[vh]);
+      const float sp = x > 20.0f ? x : logf(1.0f + expf(x));
+      decay[(size_t)t * nv + vh] = expf(-expf(a_log[vh]) * sp);
+      beta[(size_t)t * nv + vh] = 1.0f / (1.0f + expf(-bf2f(b_seq[(size_t)t * nv + vh])));
+    }
+    return;
+  }
+  const bf16* row = qkv_seq + (size_t)t * qkv_dim;
+  const float qv = bf2f(row[(size_t)kh * GK + d]), kv = bf2f(row[(size_t)nk * GK + (size_t)kh * GK + d]);
+  const float qs = block_sum(qv * qv, red);
+  const float ks = block_sum(kv * kv, red);
+  qn[((size_t)t * nk + kh) * GK + d] = qv * rsqrtf(qs + 1e-12f) * rsqrtf((float)GK);
+  kn[((size_t)t * nk + kh) * GK + d] = kv * rsqrtf(ks + 1e-12f);
+}
+
+constexpr int G2C = 32;            // state columns per CTA
+constexpr int G2T = G2C * GS;      // 128 threads: col = tid & 31, slice = tid >> 5 (32 key dims each)
+__global__ void __launch_bounds__(G2T)
+gated_delta_rule_seq2_kernel(const bf16* __restrict__ qkv_seq, const float* __restrict__ qn, const float* __restrict__ kn,
+                             const float* __restrict__ decay_s, const float* __restrict__ beta_s, float* __restrict__ state,
+                             bf16* __restrict__ out_seq, int nk, int nv, int T) {
+  __shared__ float sq[2][GK], sk[2][GK], pa[GS][G2C], pb[GS][G2C];
+  const int vh = blockIdx.x, cb = blockIdx.y, col = threadIdx.x & (G2C - 1), sl = threadIdx.x >> 5;
+  const int kh = vh * nk / nv;
+  const int qkv_dim = 2 * nk * GK + nv * GV;
+  const int vcol = cb * G2C + col;
+  pdl_wait();
+  float* st = state + ((size_t)vh * GK + (size_t)sl * GJ) * GV + vcol;
+  float s[GJ];
+#pragma unroll
+  for (int j = 0; j < GJ; ++j) s[j] = st[(size_t)j * GV];
+  // stage token 0's normalised q / k rows (128 floats each: one element per thread)
+  sq[0][threadIdx.x] = qn[((size_t)0 * nk + kh) * GK + threadIdx.x];
+  sk[0][threadIdx.x] = kn[((size_t)0 * nk + kh) * GK + threadIdx.x];
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const int cur = t & 1;
+    // requests for the next token go out before this token's dependent chain
+    float nq = 0.f, nkk = 0.f;
+    if (t + 1 < T) {
+      nq = qn[((size_t)(t + 1) * nk + kh) * GK + threadIdx.x];
+      nkk = kn[((size_t)(t + 1) * nk + kh) * GK + threadIdx.x];
+    }
+    const float decay = decay_s[(size_t)t * nv + vh], beta = beta_s[(size_t)t * nv + vh];
+    const float vv = bf2f(qkv_seq[(size_t)t * qkv_dim + (size_t)2 * nk * GK + (size_t)vh * GV + vcol]);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      s[j] *= decay;
+      acc = fmaf(s[j], sk[cur][sl * GJ + j], acc);
+    }
+    pa[sl][col] = acc;
+    __syncthreads();  // barrier 1: the four slices' k.S partial sums
+    const float delta = (vv - (pa[0][col] + pa[1][col] + pa[2][col] + pa[3][col])) * beta;
+    acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      s[j] = fmaf(delta, sk[cur][sl * GJ + j], s[j]);
+      acc = fmaf(s[j], sq[cur][sl * GJ + j], acc);
+    }
+    pb[sl][col] = acc;
+    sq[cur ^ 1][threadIdx.x] = nq;  // the other buffer: nobody reads it during this token
+    sk[cur ^ 1][threadIdx.x] = nkk;
+    __syncthreads();  // barrier 2: q.S partial sums + the next token's rows
+    if (sl == 0) out_seq[(size_t)t * nv * GV + (size_t)vh * GV + vcol] = f2bf(pb[0][col] + pb[1][col] + pb[2][col] + pb[3][col]);
+    // pa is rewritten after barrier 2, pb after the next barrier 1: both reads above are behind a barrier by then
+  }
+#pragma unroll
+  for (int j = 0; j < GJ; ++j) st[(size_t)j * GV] = s[j];
+}
+
 // ---------------------------------------------------------------- HD-256 QK prep: prefill_attention_hd256.cu:7-113,176-262
 // One warp per (head, token): lane owns 8 consecutive dims (one 16-byte vector), so the per-head RMS is a warp
 // reduction and the RoPE partner (dim +- rotary_dim/2) sits rotary_dim/16 lanes away -- no shared memory, no barrier.
@@ -346,6 +436,33 @@ int pk_b200_gated_delta_rule_prefill_recurrent(const pk_bf16* qkv_seq, const pk_
                                                int num_value_heads, int key_dim, int val_dim, int seq_len, pk_stream stream) {
   if (key_dim != GK || val_dim != GV || num_value_heads <= 0 || num_key_heads <= 0) return -1;
   if (seq_len <= 0) return 0;
+  // version 2 (token-parallel pre-pass + 2-barrier sequential kernel on 4 CTAs per head) when the thread's workspace
+  // is there (cublas_init); the sequence is cut into pieces that fit it, the state carries over in `state`.
+  ThreadState& ts = tls();
+  static const bool use_v1 = [] { const char* e = getenv("PK_GDR_SEQ"); return e && atoi(e) == 1; }();
+  const size_t per_tok = ((size_t)2 * num_key_heads * GK + 2 * num_value_heads) * sizeof(float);
+  if (!use_v1 && ts.gemm_part && ts.gemm_part_bytes >= per_tok * 64) {
+    const int max_t = (int)std::min<size_t>(ts.gemm_part_bytes / per_tok, 1 << 20);
+    for (int t0 = 0; t0 < seq_len; t0 += max_t) {
+      const int n = std::min(max_t, seq_len - t0);
+      float* qn = ts.gemm_part;
+      float* kn = qn + (size_t)n * num_key_heads * GK;
+      float* dec = kn + (size_t)n * num_key_heads * GK;
+      float* bet = dec + (size_t)n * num_value_heads;
+      const int qkv_dim = 2 * num_key_heads * GK + num_value_heads * GV;
+      const bf16* qs = (const bf16*)qkv_seq + (size_t)t0 * qkv_dim;
+      const bf16* bs = (const bf16*)b_seq + (size_t)t0 * num_value_heads;
+      const bf16* as = (const bf16*)a_seq + (size_t)t0 * num_value_heads;
+      cudaError_t e = launch(gdr_prepare_kernel, dim3(n, num_key_heads + 1), dim3(GK), 0, stream, true, qs, bs, as, (const bf16*)dt_bias, A_log,
+                             qn, kn, dec, bet, num_key_heads, num_value_heads, n);
+      if (e != cudaSuccess) return (int)e;
+      e = launch(gated_delta_rule_seq2_kernel, dim3(num_value_heads, GV / G2C), dim3(G2T), 0, stream, true, qs, (const float*)qn,
+                 (const float*)kn, (const float*)dec, (const float*)bet, state, (bf16*)out_seq + (size_t)t0 * num_value_heads * GV,
+                 num_key_heads, num_value_heads, n);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+  }
   return (int)launch(gated_delta_rule_seq_kernel, dim3(num_value_heads), dim3(GV * GS), 0, stream, true, (const bf16*)qkv_seq,
                      (const bf16*)b_seq, (const bf16*)a_seq, (const bf16*)dt_bias, A_log, state, (bf16*)out_seq, num_key_heads,
                      num_value_heads, seq_len);

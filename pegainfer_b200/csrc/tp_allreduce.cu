@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
 }
 
 // Vocab-sharded lm_head under tensor parallelism: every rank holds the (max logit, GLOBAL index) of its vocabulary
-// shard; one 16-byte {value, index, seq, seq} line per request is pushed to every peer (posted NVLink stores, the
-// sequence travels with the data) and every rank picks the same winner: highest value, lowest index on ties (the
+// shard; one 16-byte {value, seq, index, seq} line per request is pushed to every peer (posted NVLink stores; EACH
+// 8-byte half carries the sequence number, because a 16-byte store may cross the link as two 8-byte transactions and
+// a reader that validated only one half would pair a fresh sequence with a stale value -- seen on hardware) and every rank picks the same winner: highest value, lowest index on ties (the
 // single-GPU top-1 rule).  Replaces a replicated lm_head GEMV (1.24 GB per token per rank for Qwen3-8B).
 struct TpTop1Args {
   TpDev d;
@@ -190,8 +191,8 @@ __global__ void __launch_bounds__(64) tp_top1_exchange_kernel(const TpTop1Args a
   for (int p = 0; p < W; ++p)
     if (p != me) {
       uint8_t* line = a.d.stage[p] + (size_t)me * a.d.slot_bytes + off;
-      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(__float_as_uint(v)), "r"((uint32_t)gi),
-                   "r"(seq), "r"(seq)
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(__float_as_uint(v)), "r"(seq),
+                   "r"((uint32_t)gi), "r"(seq)
                    : "memory");
     }
   float bv = v;
@@ -204,9 +205,9 @@ __global__ void __launch_bounds__(64) tp_top1_exchange_kernel(const TpTop1Args a
     do {
       asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "l"(line) : "memory");
       if (++spins > (1u << 26)) __trap();
-    } while (l.z != seq || l.w != seq);
+    } while (l.y != seq || l.w != seq);
     const float ov = __uint_as_float(l.x);
-    const int oi = (int)l.y;
+    const int oi = (int)l.z;
     if (ov > bv || (ov == bv && oi < bi)) {
       bv = ov;
       bi = oi;

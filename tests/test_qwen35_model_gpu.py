@@ -34,8 +34,11 @@ def _agree(got, want, what):
     return err
 
 
-@pytest.mark.parametrize("graph", [True, False])
-def test_hybrid_prefill_decode_matches_oracle(graph):
+@pytest.mark.parametrize("graph,fused", [(True, True), (False, True), (True, False)])
+def test_hybrid_prefill_decode_matches_oracle(graph, fused, monkeypatch):
+    """fused = the default decode (norm + add prologues, rounded-SwiGLU epilogue, b/a in the in-projection launch);
+    PK_Q35_FUSED=0 = one launch per reference op."""
+    monkeypatch.setenv("PK_Q35_FUSED", "1" if fused else "0")
     cfg = QWEN35_TINY
     w = dict(iter_random_weights(cfg, seed=0))
     orc = _oracle(cfg, w)
@@ -54,7 +57,7 @@ def test_hybrid_prefill_decode_matches_oracle(graph):
         row = lg.float()
         assert float(row[sampled]) == float(row.max())
     assert m.seq_len(rid) == 37 + 8
-    print(f"\n[qwen3.5] graph={graph}: worst {worst:.2f} ulp(rowmax), {m.launches_per_step()} launches per decode step")
+    print(f"\n[qwen3.5] graph={graph} fused={fused}: worst {worst:.2f} ulp(rowmax), {m.launches_per_step()} launches per decode step")
     m.drop_request(rid)
     m.close()
 

@@ -23,6 +23,7 @@ def lib():
     l = ffi.lib()
     torch.zeros(1, device="cuda")
     l.cuda_set_device(0)
+    l.cublas_init()  # the thread workspace: the delta-rule sequence kernel takes its pre-pass version with it
     return l
 
 
@@ -261,3 +262,44 @@ def test_gated_delta_rule_prefill_recurrent(lib):
                      for t in range(T)])
     assert_bf16_close(bits(out), O.f32_to_bf16(want), 2, floor=float(np.abs(want).max()) / 64, what="gdr sequence out")
     np.testing.assert_allclose(Sd.cpu().numpy(), Sw, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("N", [1, 2])
+def test_gemv_qwen35_prologue_and_rounded_swiglu(lib, N):
+    """pk_b200_gemv_fused x_mode 3 (hidden_out = bf16(X + residual), x = (1 + w) RMSNorm of that ROUNDED sum,
+    ops/norm.rs rms_norm_offset after ops/elementwise.rs add) with the linear-attention segment split (qkv | z | [b; a]),
+    and epi 4 (act = bf16(bf16(silu(gate)) * up): Qwen3.5 keeps the unfused silu_mul's two roundings)."""
+    import ctypes as C
+    H, qkvd, zd, nv, inter = 2560, 8192, 4096, 32, 9216
+    hid, res, nw = rnd((N, H), 70, 1.0), rnd((N, H), 71, 0.3), rnd((H,), 72, 0.2)
+    W = rnd((qkvd + zd + 2 * nv, H), 73, 0.02)
+    outs = [torch.zeros((N, n), dtype=torch.bfloat16, device="cuda") for n in (qkvd, zd, 2 * nv)]
+    hout = torch.zeros((N, H), dtype=torch.bfloat16, device="cuda")
+    keep = [hid.cuda(), res.cuda(), nw.cuda(), W.cuda()]
+    g = ffi.GemvArgs()
+    g.W, g.X = keep[3].data_ptr(), keep[0].data_ptr()
+    g.Y = (C.c_void_p * 3)(*[o.data_ptr() for o in outs])
+    g.seg_rows = (C.c_int * 3)(qkvd, zd, 2 * nv)
+    g.M, g.N, g.K, g.x_mode, g.epi = qkvd + zd + 2 * nv, N, H, 3, 0
+    g.residual, g.norm_w, g.eps, g.hidden_out, g.normed_out = keep[1].data_ptr(), keep[2].data_ptr(), 1e-6, hout.data_ptr(), None
+    assert lib.pk_b200_gemv_fused(C.byref(g), st()) == 0
+    torch.cuda.synchronize()
+    summed = rb(vals(hid) + vals(res))
+    assert (bits(hout) == O.f32_to_bf16(summed)).all()
+    want = O.f32_to_bf16(rms_norm_offset(summed, vals(nw), 1e-6) @ vals(W).T)
+    got = np.concatenate([bits(o) for o in outs], axis=1)
+    assert_bf16_close(got, want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what="x_mode 3 in-projection")
+    # epi 4 on a gate | up matrix
+    Wgu, x = rnd((2 * inter, H), 74, 0.02), rnd((N, H), 75, 1.0)
+    act = torch.zeros((N, inter), dtype=torch.bfloat16, device="cuda")
+    keep2 = [Wgu.cuda(), x.cuda(), torch.zeros((N, H), dtype=torch.bfloat16, device="cuda")]
+    g2 = ffi.GemvArgs()
+    g2.W, g2.X = keep2[0].data_ptr(), keep2[1].data_ptr()
+    g2.Y = (C.c_void_p * 3)(act.data_ptr(), None, None)
+    g2.seg_rows = (C.c_int * 3)(inter, 0, 0)
+    g2.M, g2.N, g2.K, g2.x_mode, g2.epi = inter, N, H, 0, 4
+    assert lib.pk_b200_gemv_fused(C.byref(g2), st()) == 0
+    torch.cuda.synchronize()
+    gu = rb(vals(x) @ vals(Wgu).T)
+    want = O.f32_to_bf16(rb(silu(gu[:, :inter])) * gu[:, inter:])
+    assert_bf16_close(bits(act), want, 2, floor=float(np.abs(f32(want)).max()) / 64, frac_exact=0.85, what="epi 4 rounded swiglu")
