@@ -336,14 +336,24 @@ int launch_prefill_tc(const bf16* q, bf16* out, const bf16* k_base, const bf16* 
                       const int* page_indptr, const int* last_page_len, const int* q_indptr, int seq_len, int batch_size,
                       int nq, int nkv, int page_size, int64_t stride_page, float sm_scale_log2, cudaStream_t stream);
 
-// PK_PREFILL_ATTN = tc (default) | legacy: tcgen05/TMEM kernel or the mma.sync kernel for the paged batch-prefill entry.
+// prefill_attention_tc2.cu
+int launch_prefill_tc2(const bf16* q, bf16* out, const bf16* k_base, const bf16* v_base, const int* page_indices,
+                       const int* page_indptr, const int* last_page_len, const int* q_indptr, int seq_len, int batch_size, int nq,
+                       int nkv, int page_size, int64_t stride_page, float sm_scale_log2, cudaStream_t stream);
+
+// PK_PREFILL_ATTN = tc2 (default: two query tiles per CTA, O and P in TMEM) | tc (one tile per CTA, O in registers) |
+// legacy (the mma.sync kernel) for the paged batch-prefill entry.  Read per call: the A/B tools flip it in-process.
 static int prefill_attn_impl() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PK_PREFILL_ATTN");
-    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
-  }
-  return v;
+  const char* e = getenv("PK_PREFILL_ATTN");
+  if (e && strcmp(e, "legacy") == 0) return 0;
+  if (e && strcmp(e, "tc") == 0) return 1;
+  return 2;
+}
+static int launch_prefill_tensor(int impl, const bf16* q, bf16* out, const bf16* k_base, const bf16* v_base, const int* page_indices,
+                                 const int* page_indptr, const int* last_page_len, const int* q_indptr, int seq_len, int batch_size,
+                                 int nq, int nkv, int page_size, int64_t stride_page, float sm_scale_log2, cudaStream_t stream) {
+  return (impl == 2 ? launch_prefill_tc2 : launch_prefill_tc)(q, out, k_base, v_base, page_indices, page_indptr, last_page_len, q_indptr,
+                                                              seq_len, batch_size, nq, nkv, page_size, stride_page, sm_scale_log2, stream);
 }
 }  // namespace pk
 
@@ -387,8 +397,8 @@ int batch_prefill_paged_cuda_with_cta_tile_q(
                          head_dim, cta_tile_q_override) == 0)
     return -1;  // invalid tile override, as the reference
   if (seq_len <= 0 || batch_size <= 0) return 0;
-  if (prefill_attn_impl() == 1 && q_indptr && page_size == 16 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0) {
-    const int rc = launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+  if (prefill_attn_impl() >= 1 && q_indptr && page_size == 16 && num_kv_heads > 0 && num_qo_heads % num_kv_heads == 0) {
+    const int rc = launch_prefill_tensor(prefill_attn_impl(), (const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
                                      (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d,
                                      q_indptr, seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
                                      sm_scale * 1.44269504088896340736f, stream);
@@ -445,10 +455,11 @@ int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf1
                                  float sm_scale, pk_stream stream) {
   if (head_dim != PHD || !q_indptr || num_kv_heads <= 0 || num_qo_heads % num_kv_heads != 0 || page_size != 16) return -1;
   if (seq_len <= 0 || batch_size <= 0) return 0;
-  const int rc = launch_prefill_tc((const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
-                                   (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d,
-                                   q_indptr, seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
-                                   sm_scale * 1.44269504088896340736f, stream);
+  const int impl = prefill_attn_impl() == 1 ? 1 : 2;
+  const int rc = launch_prefill_tensor(impl, (const bf16*)q, (bf16*)output, (const bf16*)kv_data + k_offset_elems,
+                                       (const bf16*)kv_data + v_offset_elems, page_indices, page_indptr, last_page_len_d,
+                                       q_indptr, seq_len, batch_size, num_qo_heads, num_kv_heads, page_size, stride_page,
+                                       sm_scale * 1.44269504088896340736f, stream);
   return rc == -2 ? -1 : rc;
 }
 

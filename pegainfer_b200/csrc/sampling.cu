@@ -116,6 +116,17 @@ void argmax_cuda(const pk_bf16* x, int* out, int n, pk_stream stream) {
   pk::launch(pk::argmax_kernel, dim3(1), dim3(1024), 0, stream, true, (const pk::bf16*)x, out, n);
 }
 
+}  // extern "C"
+namespace pk {
+// small-row path of flashinfer_top1_cuda: the single-CTA arg-max writes only the index; the winner's value is part of
+// the contract too (the vocab-sharded TP exchange compares it across ranks)
+__global__ void top1_value_gather_kernel(const bf16* logits, const int* idx, bf16* value) {
+  pdl_wait();
+  if (threadIdx.x == 0) value[0] = logits[idx[0]];
+}
+}  // namespace pk
+extern "C" {
+
 void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
                           uint8_t* row_states_scratch, int* output, int vocab_size,
                           pk_stream stream) {
@@ -123,6 +134,9 @@ void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
   const bool al = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
   if (!al || row_states_scratch == nullptr || vocab_size < 8192) {
     argmax_cuda(logits, output, vocab_size, stream);
+    if (top1_value_scratch)
+      pk::launch(pk::top1_value_gather_kernel, dim3(1), dim3(32), 0, stream, true, (const pk::bf16*)logits, (const int*)output,
+                 (pk::bf16*)top1_value_scratch);
     return;
   }
   int grid = (vocab_size + 2047) / 2048;

@@ -430,6 +430,9 @@ def test_top1_matches_argmax(lib, n):
         assert float(xf[got]) == float(xf[want])  # the reference's radix top-1 leaves tie ORDER undefined
         if lib is get_lib("b200"):
             assert got == want  # ours: lowest index
+            # ours also returns the winner's VALUE (both the multi-CTA and the small-row path): the vocab-sharded
+            # tensor-parallel top-1 exchange compares it across ranks
+            assert float(val[0].float()) == float(xf[want])
 
 
 # ------------------------------------------------------------------ non-greedy sampling
@@ -616,11 +619,17 @@ def test_decode_attention_prefetch_rejects_bad_spans():
 
 
 # ------------------------------------------------------------------ tcgen05 prefill attention (direct entry)
+@pytest.mark.parametrize("impl", ["tc2", "tc"])
 @pytest.mark.parametrize("starts,lens,nq,nkv", [([0], [128], 32, 8), ([0, 0, 0], [33, 100, 5], 32, 8), ([40], [60], 32, 8),
-                                                ([0], [300], 4, 1), ([100, 0], [700, 129], 32, 8)])
-def test_prefill_attention_tc(starts, lens, nq, nkv):
-    """The tcgen05/TMEM flash-attention kernel (TMA page loads, MN-major V operand) against the oracle, same
-    tolerance as the mma.sync kernel behind the ABI entry (test_batch_prefill_paged)."""
+                                                ([0], [300], 4, 1), ([100, 0], [700, 129], 32, 8), ([0], [256], 8, 2),
+                                                ([0], [257], 8, 2), ([900], [300], 8, 2), ([0], [1536], 4, 1),
+                                                ([0, 3, 250], [1, 130, 390], 8, 2)])
+def test_prefill_attention_tc(starts, lens, nq, nkv, impl, monkeypatch):
+    """The tcgen05/TMEM flash-attention kernels (TMA page loads, MN-major V operand; tc2 = two query tiles per CTA with O
+    and P in tensor memory, the default; tc = one tile per CTA) against the oracle, same tolerance as the mma.sync
+    kernel behind the ABI entry (test_batch_prefill_paged).  Cases cover a single tile, a tile pair with the second
+    tile short by one / long by one token, chunked prefill (causal offset 900), 12 KV blocks, and a ragged batch."""
+    monkeypatch.setenv("PK_PREFILL_ATTN", impl)
     lib = get_lib("b200")
     hd, layer, bs = 128, 1, len(lens)
     kv_lens = [s + n for s, n in zip(starts, lens)]
