@@ -104,7 +104,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
   float* xch = reinterpret_cast<float*>(bars + 14);  // [2 parities][2 halves][128 rows] row maxima / denominators
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
+  const int head = blockIdx.x;  // heads vary fastest: all heads' heaviest tiles are scheduled first
   const int kvh = head / (a.nq / a.nkv);
 
   // ---- locate (request, 128-token tile): late (heavy) tiles first ----
@@ -112,7 +112,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __g
   {
     int total_tiles = 0;
     for (int i = 0; i < a.batch_size; ++i) total_tiles += (a.q_indptr[i + 1] - a.q_indptr[i] + TQ - 1) / TQ;
-    int idx = total_tiles - 1 - (int)blockIdx.x;
+    int idx = total_tiles - 1 - (int)blockIdx.y;
     if (idx < 0) return;
     for (int i = 0; i < a.batch_size; ++i) {
       const int len = a.q_indptr[i + 1] - a.q_indptr[i];
@@ -390,7 +390,7 @@ int launch_prefill_tc(const bf16* q, bf16* out, const bf16* k_base, const bf16* 
     cfg = true;
   }
   const int tiles = (seq_len + TQ - 1) / TQ + batch_size;  // upper bound; surplus CTAs exit at once
-  return (int)launch(prefill_attention_tc_kernel, dim3(tiles, nq), dim3(T_THREADS), smem, stream, true, mk, mv, a);
+  return (int)launch(prefill_attention_tc_kernel, dim3(nq, tiles), dim3(T_THREADS), smem, stream, true, mk, mv, a);
 }
 
 }  // namespace pk

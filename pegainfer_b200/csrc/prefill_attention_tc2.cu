@@ -36,8 +36,8 @@ constexpr int TKV = 128;               // kv tokens per block
 constexpr int PAGE = 16;               // tokens per page
 constexpr int HALF_BYTES = 128 * 128;  // one 64-column half of a [128 x 128] bf16 tile
 constexpr int TILE_B = 2 * HALF_BYTES;
-constexpr int W_CORR = 8, W_MMA = 12, W_LOAD = 13;
-constexpr int NTHREADS = 14 * 32;
+constexpr int W_CORR = 8, W_MMA = 12, W_LOAD = 14;  // warps 12 / 13 issue the MMAs of tile 0 / tile 1
+constexpr int NTHREADS = 15 * 32;
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Args {
@@ -49,12 +49,35 @@ struct Args {
   const int* q_indptr;
   int seq_len, batch_size, nq, nkv;
   float sm_scale_log2;
+  int dbg;  // PK_FA2_DBG ablation bits (timing experiments only; results are wrong when set): 1 no P V MMAs, 2 no S MMAs, 4 no exponentials, 8 no O rescale, 32 trace, 64 skip the first TMEM read of the max phase
 };
+
+// PK_FA2_DBG bit 32: the heaviest CTA of head 0 records %clock64 at the hand-over points of tile 0 (tools/fa2_trace.py)
+__device__ unsigned long long g_fa2_trace[3 * 128 * 8];
+#define FA2_TRACE(role, j, slot)                                                                                  \
+  do {                                                                                                            \
+    if (trace_on && lane == 0 && (j) < 128) g_fa2_trace[((role) * 128 + (j)) * 8 + (slot)] = clock64();           \
+  } while (0)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// {x0, x1} * s + c on the packed fp32 pipe (FFMA2, scalars broadcast)
+__device__ __forceinline__ void fma2(float& x0, float& x1, float s, float c) {
+  unsigned long long v, sv, cv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(sv) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cv) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(v), "l"(sv), "l"(cv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(v));
+}
+// acc0 += lo bf16 of pk, acc1 += hi bf16 of pk, exactly (fp32 accumulate of the ROUNDED values, FHADD.BF16: no unpack)
+__device__ __forceinline__ void add_bf16_pair(float& acc0, float& acc1, uint32_t pk) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+      : "+f"(acc0), "+f"(acc1)
+      : "r"(pk));
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
@@ -70,7 +93,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 // A hung barrier becomes a trap (reported as a launch failure) instead of a wedged GPU.
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-    if (spins > (1u << 26)) __trap();
+    if (spins > (1u << 24)) __trap();
 }
 __device__ __forceinline__ uint32_t sw_off(int r, int c16) {
   return (uint32_t)((c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
@@ -109,6 +132,13 @@ __device__ __forceinline__ void tmem_ld_wait_2x32(uint32_t* a, uint32_t* b) {
                :
                : "memory");
 }
+// one lane of the (converged) warp; the compiler knows a single thread is active under this predicate, so the
+// uniform-register operands of tcgen05.mma / commit need no per-thread waterfall (unlike `lane == 0`)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -123,9 +153,8 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
   uint64_t* v_full = bars + 4;        // [2]
   uint64_t* v_empty = bars + 6;       // [2] tcgen05.commit after the last P V of the block
   uint64_t* s_full = bars + 8;        // [tile] S(j) complete                        MMA -> softmax
-  uint64_t* p_ready = bars + 10;      // [tile] P(j) stored in TMEM (128 arrivals)    softmax -> MMA
+  uint64_t* po_ready = bars + 10;     // [tile] P(j) stored AND O scaled by alpha(j) (4 + 4 warp arrivals)  softmax, correction -> MMA
   uint64_t* a_ready = bars + 12;      // [tile] alpha(j) published (128 arrivals)     softmax -> correction
-  uint64_t* o_ready = bars + 14;      // [tile] O scaled by alpha(j) (128 arrivals)   correction -> MMA
   uint64_t* pv_done = bars + 16;      // [tile] P V(j) complete                       MMA -> correction
   uint64_t* d_ready = bars + 18;      // [tile] final denominators published (128)   softmax -> correction
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
@@ -133,7 +162,7 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
   float* denom_s = alpha_s + 2 * TQ;                     // [tile][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
+  const int head = blockIdx.x;  // heads vary fastest: every head's heaviest tile pair is scheduled before any lighter one
   const int kvh = head / (a.nq / a.nkv);
 
   // ---- locate (request, 256-token tile pair): late (heavy) pairs first ----
@@ -141,7 +170,7 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
   {
     int total = 0;
     for (int i = 0; i < a.batch_size; ++i) total += (a.q_indptr[i + 1] - a.q_indptr[i] + 2 * TQ - 1) / (2 * TQ);
-    int idx = total - 1 - (int)blockIdx.x;
+    int idx = total - 1 - (int)blockIdx.y;
     if (idx < 0) return;
     for (int i = 0; i < a.batch_size; ++i) {
       const int len = a.q_indptr[i + 1] - a.q_indptr[i];
@@ -168,15 +197,14 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full + s, 1);
-      mbar_init(k_empty + s, 1);
+      mbar_init(k_empty + s, 2);  // one arrival per tile (a tile that does not read the block is arrived for)
       mbar_init(v_full + s, 1);
-      mbar_init(v_empty + s, 1);
+      mbar_init(v_empty + s, 2);
       mbar_init(s_full + s, 1);
-      mbar_init(p_ready + s, TQ);
-      mbar_init(a_ready + s, TQ);
-      mbar_init(o_ready + s, TQ);
+      mbar_init(po_ready + s, 8);  // one elected arrival per warp: 4 softmax + 4 correction
+      mbar_init(a_ready + s, 4);
       mbar_init(pv_done + s, 1);
-      mbar_init(d_ready + s, TQ);
+      mbar_init(d_ready + s, 4);
     }
     mbar_fence_init();
   }
@@ -184,20 +212,26 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
   pdl_launch_dependents();
   pdl_wait();  // q (and the appended K/V rows) come from the previous kernels
 
-  // ---- both Q tiles -> swizzled smem (all threads), rows past the request are zero ----
-  for (int idx = threadIdx.x; idx < 2 * TQ * 16; idx += NTHREADS) {
-    const int r = idx >> 4, c = idx & 15;  // r in [0, 256)
-    const bool valid = t0 + r < qo_len;
-    const bf16* src = a.q + ((size_t)(q_start + (valid ? t0 + r : 0)) * a.nq + head) * HD + c * 8;
-    cp_async16(smem_u32(Qs) + (uint32_t)((r >> 7) * TILE_B) + sw_off(r & 127, c), src, valid);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  fence_proxy_async_smem();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool trace_on = (a.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0;
+
+  if (warp != W_LOAD) {
+    // ---- both Q tiles -> swizzled smem (every warp but the loader, whose K / V loads are already in flight), rows past
+    // the request are zero ----
+    for (int idx = threadIdx.x; idx < 2 * TQ * 16; idx += NTHREADS - 32) {
+      const int r = idx >> 4, c = idx & 15;  // r in [0, 256)
+      const bool valid = t0 + r < qo_len;
+      const bf16* src = a.q + ((size_t)(q_start + (valid ? t0 + r : 0)) * a.nq + head) * HD + c * 8;
+      cp_async16(smem_u32(Qs) + (uint32_t)((r >> 7) * TILE_B) + sw_off(r & 127, c), src, valid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS - 32) : "memory");
+  }
 
   if (warp == W_LOAD) {
     // =========================== TMA loader ===========================
@@ -228,84 +262,107 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
         }
       }
     }
-  } else if (warp == W_MMA) {
-    // =========================== MMA issuer ===========================
-    constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TKV >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
-    constexpr uint32_t idesc_pv = idesc_s | (1u << 16);  // B (= V) MN-major
-    auto issue_s = [&](int i, int j) {
-      const int s = j & 1;
-      wait_or_trap(k_full + s, (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t q_addr = smem_u32(Qs) + (uint32_t)(i * TILE_B);
-        const uint32_t k_addr = smem_u32(KVs + (size_t)s * 2 * TILE_B);
-        const uint32_t d = tmem_base + (uint32_t)(i * TKV);
+  } else if (warp >= W_MMA) {
+    // =========================== MMA issuers: one single-thread pipeline per tile ===========================
+    // The trace of the one-issuer version (tools/fa2_trace.py) showed the issuing thread busy ~100 % of the time: every
+    // tcgen05.mma stalls until the tensor queue has room, so issue time ~ execution time, and the waits / commits
+    // between the batches (~320 cycles each) left the pipe dry.  Two issuers (disjoint TMEM regions) interleave in the
+    // hardware queue, the K / V arrivals are checked before the P hand-over, and the descriptors are precomputed.
+    {
+      const int i = warp - W_MMA;
+      const int n_i = nblk(i), n_o = nblk(1 - i);
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TKV >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+      constexpr uint32_t idesc_pv = idesc_s | (1u << 16);  // B (= V) MN-major
+      const uint64_t q_desc = make_sw128_desc(smem_u32(Qs) + (uint32_t)(i * TILE_B));
+      const uint32_t t_sp = tmem_base + (uint32_t)(i * TKV);           // S, and P over its first 64 columns
+      const uint32_t t_o = tmem_base + (uint32_t)(2 * TKV + i * HD);  // O
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint64_t k_desc = make_sw128_desc(smem_u32(KVs + (size_t)s * 2 * TILE_B));
+        if (elect_one()) {
+          if (!(a.dbg & 2)) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t o = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-          umma_bf16(d, make_sw128_desc(q_addr + o), make_sw128_desc(k_addr + o), idesc_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint64_t o = (uint64_t)((k >> 2) * (HALF_BYTES >> 4) + (k & 3) * 2);  // descriptor address field: 16-byte units
+              umma_bf16(t_sp, q_desc + o, k_desc + o, idesc_s, k > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(s_full + i);
+          umma_commit(k_empty + s);
+          if (j >= n_o) umma_commit(k_empty + s);  // the other tile does not read K(j): arrive for it
         }
-        umma_commit(s_full + i);
-        if (i == 1 || j >= nblk1) umma_commit(k_empty + s);  // last reader of K(j)
+        __syncwarp();
+        if (i == 0) FA2_TRACE(1, j, 5);
+      };
+      if (n_i > 0) {
+        // Stagger the tiles by half a block: tile 1 starts when tile 0 has finished its first softmax, so that one
+        // tile's exponentials run under the other's MMAs instead of both contending for the MUFU and then for the
+        // tensor pipe (nothing re-synchronises them afterwards; measured with tools/fa2_trace.py).
+        if (i == 1 && !(a.dbg & 128)) wait_or_trap(po_ready + 0, 0);
+        wait_or_trap(k_full, 0);
+        tc_fence_after();
+        issue_s(0);
       }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int i, int j) {
-      const int s = j & 1;
-      wait_or_trap(p_ready + i, (uint32_t)(j & 1));
-      if (j > 0) wait_or_trap(o_ready + i, (uint32_t)((j - 1) & 1));
-      wait_or_trap(v_full + s, (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t v_addr = smem_u32(KVs + (size_t)s * 2 * TILE_B) + TILE_B;
-        const uint32_t d = tmem_base + (uint32_t)(2 * TKV + i * HD);
-        const uint32_t p_t = tmem_base + (uint32_t)(i * TKV);
-        const int ksteps = min(TKV / 16, np - j * (TKV / PAGE));  // one k-step = one 16-token page
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(d, p_t + (uint32_t)(k * 8), make_sw128_mn_desc(v_addr + (uint32_t)(k * 2048), HALF_BYTES, 1024), idesc_pv,
-                       (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(pv_done + i);
-        if (i == 1 || j >= nblk1) umma_commit(v_empty + s);  // last reader of V(j)
+      for (int j = 0; j < n_i; ++j) {
+        const int s = j & 1;
+        // operands first (long since there in steady state), then the hand-over that is on the critical path
+        wait_or_trap(v_full + s, (uint32_t)((j >> 1) & 1));
+        if (j + 1 < n_i) wait_or_trap(k_full + (s ^ 1), (uint32_t)(((j + 1) >> 1) & 1));
+        if (i == 0) FA2_TRACE(1, j, 0);
+        wait_or_trap(po_ready + i, (uint32_t)(j & 1));  // P(j) stored and O scaled by alpha(j)
+        tc_fence_after();
+        if (i == 0) FA2_TRACE(1, j, 1);
+        const uint64_t v_desc = make_sw128_mn_desc(smem_u32(KVs + (size_t)s * 2 * TILE_B) + TILE_B, HALF_BYTES, 1024);
+        const int ksteps = (a.dbg & 1) ? 0 : min(TKV / 16, np - j * (TKV / PAGE));  // one k-step = one 16-token page
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TKV / 16; ++k)
+            if (k < ksteps) umma_bf16_ts(t_o, t_sp + (uint32_t)(k * 8), v_desc + (uint64_t)(k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(pv_done + i);
+          umma_commit(v_empty + s);
+          if (j >= n_o) umma_commit(v_empty + s);
+        }
+        __syncwarp();
+        if (i == 0) FA2_TRACE(1, j, 3);
+        if (j + 1 < n_i) issue_s(j + 1);  // in order behind P V(j): it overwrites the S / P columns P V(j) reads
       }
-      __syncwarp();
-    };
-    for (int i = 0; i < 2; ++i)
-      if (nblk(i) > 0) issue_s(i, 0);
-    for (int j = 0; j < nb; ++j)
-      for (int i = 0; i < 2; ++i) {
-        if (j < nblk(i)) issue_pv(i, j);
-        if (j + 1 < nblk(i)) issue_s(i, j + 1);
-      }
+    }
   } else if (warp >= W_CORR) {
     // =========================== correction + epilogue ===========================
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    for (int j = 1; j < nb; ++j)
+    for (int j = 0; j < nb; ++j)
       for (int i = 0; i < 2; ++i) {
         if (j >= nblk(i)) continue;
-        wait_or_trap(a_ready + i, (uint32_t)((j - 1) & 1));
-        const float alpha = alpha_s[i * TQ + r];
-        const bool need = !__all_sync(0xffffffffu, alpha == 1.0f);
-        wait_or_trap(pv_done + i, (uint32_t)((j - 1) & 1));  // O holds blocks < j
-        tc_fence_after();
-        if (need) {
-          const uint32_t t_o = lane_base + (uint32_t)(2 * TKV + i * HD);
+        if (j > 0) {
+          wait_or_trap(a_ready + i, (uint32_t)((j - 1) & 1));
+          if (i == 0 && q4 == 0) FA2_TRACE(2, j, 0);
+          const float alpha = alpha_s[i * TQ + r];
+          const bool need = !__all_sync(0xffffffffu, alpha == 1.0f);
+          wait_or_trap(pv_done + i, (uint32_t)((j - 1) & 1));  // O holds blocks < j
+          tc_fence_after();
+          if (i == 0 && q4 == 0) FA2_TRACE(2, j, 1);
+          if (need && !(a.dbg & 8)) {
+            const uint32_t t_o = lane_base + (uint32_t)(2 * TKV + i * HD);
 #pragma unroll
-          for (int c = 0; c < HD; c += 64) {
-            uint32_t t[64];
-            tmem_ld32_nowait(t_o + c, t);
-            tmem_ld32_nowait(t_o + c + 32, t + 32);
-            tmem_ld_wait64(t);
+            for (int c = 0; c < HD; c += 64) {
+              uint32_t t[64];
+              tmem_ld32_nowait(t_o + c, t);
+              tmem_ld32_nowait(t_o + c + 32, t + 32);
+              tmem_ld_wait64(t);
 #pragma unroll
-            for (int x = 0; x < 64; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
-            tmem_st32(t_o + c, t);
-            tmem_st32(t_o + c + 32, t + 32);
+              for (int x = 0; x < 64; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
+              tmem_st32(t_o + c, t);
+              tmem_st32(t_o + c + 32, t + 32);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
+          tc_fence_before();
         }
-        tc_fence_before();
-        mbar_arrive(o_ready + i);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(po_ready + i);  // block 0: nothing to scale, the MMA warp still expects both halves of the hand-over
+        if (i == 0 && q4 == 0) FA2_TRACE(2, j, 2);
       }
     // epilogue: O / d -> bf16 -> global, one row per thread
     for (int i = 0; i < 2; ++i) {
@@ -347,13 +404,16 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
     for (int j = 0; j < n_i; ++j) {
       wait_or_trap(s_full + i, (uint32_t)(j & 1));
       tc_fence_after();
+      if (warp == 0) FA2_TRACE(0, j, 0);
       const bool masked = !__all_sync(0xffffffffu, j * TKV + TKV - 1 <= lim);  // warp-uniform
       // ---- row maximum in raw score units (the scale is positive): columns 64..127 first (dropped), then 0..63 (kept) ----
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       uint32_t v[64];
-      tmem_ld32_nowait(t_s + 64, v);
-      tmem_ld32_nowait(t_s + 96, v + 32);
-      tmem_ld_wait64(v);
+      if (!(a.dbg & 64)) {
+        tmem_ld32_nowait(t_s + 64, v);
+        tmem_ld32_nowait(t_s + 96, v + 32);
+        tmem_ld_wait64(v);
+      }
       if (masked) {
         const int c0 = j * TKV + 64;
 #pragma unroll
@@ -381,57 +441,60 @@ prefill_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_k, const __
       const float ref = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2(m - ref);  // m = -inf -> 0
       m = m_new;
+      if (warp == 0) FA2_TRACE(0, j, 1);
       if (j > 0) {
         alpha_s[i * TQ + r] = alpha;
-        mbar_arrive(a_ready + i);  // release: the correction warps read alpha after their wait
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready + i);  // release: the correction warps read alpha after their wait
       }
-      // ---- P = bf16(exp2(s * scale - ref)); the denominator sums the ROUNDED values ----
+      if (a.dbg & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(po_ready + i);
+        continue;
+      }
+      // ---- P = bf16(exp2(s * scale - ref)); the denominator sums the ROUNDED values (FHADD.BF16 straight off the pair) ----
+      const float nref = -ref;
+      float ds4[4] = {0.f, 0.f, 0.f, 0.f};
+      auto p_pair = [&](uint32_t u0, uint32_t u1, int x) -> uint32_t {
+        float s0 = __uint_as_float(u0), s1 = __uint_as_float(u1);
+        fma2(s0, s1, scale, nref);
+        const uint32_t pk = pack_bf16(ex2(s0), ex2(s1));
+        add_bf16_pair(ds4[(x & 1) * 2], ds4[(x & 1) * 2 + 1], pk);
+        return pk;
+      };
       uint32_t w[32];
       tmem_ld32_nowait(t_s + 64, w);  // columns 64..95 again (still intact): in flight under the first half's exponentials
-      float ds4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int x = 0; x < 32; ++x) {
-        const uint32_t pk = pack_bf16(ex2(fmaf(__uint_as_float(v[2 * x]), scale, -ref)), ex2(fmaf(__uint_as_float(v[2 * x + 1]), scale, -ref)));
-        ds4[x & 3] += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-        v[x] = pk;
-      }
+      for (int x = 0; x < 32; ++x) v[x] = p_pair(v[2 * x], v[2 * x + 1], x);
       tmem_st32(t_s, v);  // P columns 0..31 = kv 0..63 of the block (over S columns already consumed)
       tmem_ld32_nowait(t_s + 96, v + 32);
       tmem_ld_wait_2x32(w, v + 32);
-      {
+      if (masked) {
         const int c0 = j * TKV + 64;
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          float s0 = __uint_as_float(w[2 * x]), s1 = __uint_as_float(w[2 * x + 1]);
-          if (masked) {
-            if (c0 + 2 * x > lim) s0 = -INFINITY;
-            if (c0 + 2 * x + 1 > lim) s1 = -INFINITY;
-          }
-          const uint32_t pk = pack_bf16(ex2(fmaf(s0, scale, -ref)), ex2(fmaf(s1, scale, -ref)));
-          ds4[x & 3] += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-          w[x] = pk;
-        }
-#pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          float s0 = __uint_as_float(v[32 + 2 * x]), s1 = __uint_as_float(v[32 + 2 * x + 1]);
-          if (masked) {
-            if (c0 + 32 + 2 * x > lim) s0 = -INFINITY;
-            if (c0 + 32 + 2 * x + 1 > lim) s1 = -INFINITY;
-          }
-          const uint32_t pk = pack_bf16(ex2(fmaf(s0, scale, -ref)), ex2(fmaf(s1, scale, -ref)));
-          ds4[x & 3] += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-          w[16 + x] = pk;
+        for (int x = 0; x < 32; ++x) {
+          if (c0 + x > lim) w[x] = 0xff800000u;
+          if (c0 + 32 + x > lim) v[32 + x] = 0xff800000u;
         }
       }
+#pragma unroll
+      for (int x = 0; x < 16; ++x) w[x] = p_pair(w[2 * x], w[2 * x + 1], x);
+#pragma unroll
+      for (int x = 0; x < 16; ++x) w[16 + x] = p_pair(v[32 + 2 * x], v[32 + 2 * x + 1], x);
       tmem_st32(t_s + 32, w);  // P columns 32..63 = kv 64..127
+      if (warp == 0) FA2_TRACE(0, j, 2);
       tmem_st_wait();
       d = fmaf(d, alpha, (ds4[0] + ds4[1]) + (ds4[2] + ds4[3]));
       tc_fence_before();
-      mbar_arrive(p_ready + i);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(po_ready + i);
+      if (warp == 0) FA2_TRACE(0, j, 3);
     }
     if (n_i > 0) {
       denom_s[i * TQ + r] = d;
-      mbar_arrive(d_ready + i);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_ready + i);
     }
   }
   tc_fence_before();
@@ -457,6 +520,12 @@ static bool make_kv_map(CUtensorMap* map, const bf16* base, int nkv, int64_t str
 
 }  // namespace fa2
 
+// copies the PK_FA2_DBG=32 trace ([role 0 softmax / 1 MMA / 2 correction][block][8] clock64 values) to the host
+extern "C" int pk_b200_fa2_trace_copy(void* host_out, int bytes) {
+  if (bytes > (int)sizeof(fa2::g_fa2_trace)) bytes = (int)sizeof(fa2::g_fa2_trace);
+  return (int)cudaMemcpyFromSymbol(host_out, fa2::g_fa2_trace, bytes);
+}
+
 // Launch for the paged batch-prefill entry (prefill_attention.cu dispatches here).  Returns cudaError as int, -2 when
 // the pool cannot be described by a TMA tensor map (the caller falls back).
 int launch_prefill_tc2(const bf16* q, bf16* out, const bf16* k_base, const bf16* v_base, const int* page_indices,
@@ -473,6 +542,10 @@ int launch_prefill_tc2(const bf16* q, bf16* out, const bf16* k_base, const bf16*
   a.page_indices = page_indices; a.page_indptr = page_indptr; a.last_page_len = last_page_len; a.q_indptr = q_indptr;
   a.seq_len = seq_len; a.batch_size = batch_size; a.nq = nq; a.nkv = nkv;
   a.sm_scale_log2 = sm_scale_log2;
+  {
+    const char* e = getenv("PK_FA2_DBG");
+    a.dbg = e ? atoi(e) : 0;
+  }
   constexpr size_t smem = 6 * TILE_B + 1024 + 256 + 2048;
   static thread_local bool cfg = false;
   if (!cfg) {
@@ -480,7 +553,7 @@ int launch_prefill_tc2(const bf16* q, bf16* out, const bf16* k_base, const bf16*
     cfg = true;
   }
   const int pairs = (seq_len + 2 * TQ - 1) / (2 * TQ) + batch_size;  // upper bound; surplus CTAs exit at once
-  return (int)launch(prefill_attention_tc2_kernel, dim3(pairs, nq), dim3(NTHREADS), smem, stream, true, mk, mv, a);
+  return (int)launch(prefill_attention_tc2_kernel, dim3(nq, pairs), dim3(NTHREADS), smem, stream, true, mk, mv, a);
 }
 
 }  // namespace pk

@@ -646,6 +646,9 @@ def test_prefill_attention_tc(starts, lens, nq, nkv, impl, monkeypatch):
     assert rc == 0
     want = O.batch_prefill_paged(bits(q), bits(pg.kv), L.k_offset(layer), L.v_offset(layer), pg.pi, pg.ip, pg.lpl,
                                  q_indptr, nq, nkv, hd, 16, L.page_stride, sm)
+    from tests.helpers import ulp_err
+    e = ulp_err(bits(out).ravel(), np.asarray(want).ravel(), float(np.abs(f32(want)).max()) / 32)
+    print(f"\n[prefill attention {impl}] lens {lens} starts {starts}: max err {e.max():.2f} ulp, {float((e == 0).mean()):.4f} bit-exact")
     assert_bf16_close(bits(out), want, 8, floor=float(np.abs(f32(want)).max()) / 32, what="tc prefill attn")
     assert lib.pk_b200_prefill_attention_tc(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
                                             p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(q_indptr)), nq, nkv, hd, 32,

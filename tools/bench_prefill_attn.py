@@ -33,7 +33,7 @@ def timeit(fn, iters=20):
 i32 = lambda a: torch.tensor(a, dtype=torch.int32, device="cuda")
 nq, nkv, hd = 32, 8, 128
 impls = sys.argv[1:] or ["tc2", "tc", "legacy"]
-for T in (128, 512, 2048, 8192):
+for T in [int(x) for x in os.environ.get("PK_T", "128,512,2048,8192").split(",")]:
     pages = T // 16 + 1
     stride = 2 * 16 * nkv * hd
     kv = torch.randn(((pages + 2) * stride,), device="cuda").to(torch.bfloat16)
