@@ -111,11 +111,12 @@ def test_qwen3_4b_config1_vs_live_oracle(w4b, cfg1_oracle, name, kw, steps):
     n = len(toks) if steps is None else min(steps, len(toks))
     m = _model(w4b, num_pages=64, **kw)
     got = _teacher_forced(m, synthetic_prompt(128), toks[:n])
-    worst, same = 0.0, 0
+    worst, same, same_at = 0.0, 0, []
     for step, (g, w_) in enumerate(zip(got, want[:n + 1])):
         ok, info = logits_agree(g, w_, TOL_ULP)
         worst = max(worst, info["err"] / (info["tol"] / TOL_ULP))
         same += info["same_argmax"]
+        same_at.append(bool(info["same_argmax"]))
         assert ok, f"{name} config-1 step {step}: {info}"
     # free-running greedy sequence vs the oracle's: reported, and must at least start together
     free, _, _ = m.generate(synthetic_prompt(128), n + 1)
@@ -124,7 +125,10 @@ def test_qwen3_4b_config1_vs_live_oracle(w4b, cfg1_oracle, name, kw, steps):
     div = next((i for i, (a, b) in enumerate(zip(free, oracle_seq)) if a != b), None)
     print(f"\n[fullsize] {name} config 1: {n + 1} steps, worst |dlogit| = {worst:.2f} ulp(rowmax), arg-max equal "
           f"{same}/{n + 1}, free-running first divergence: {div}")
-    assert div is None or div >= 1
+    # Up to the first divergence the free-running and the teacher-forced runs see the same tokens, so a divergence at
+    # step `div` must be one of the near-ties the parity rule accepted there (top-1/top-2 gap <= 2 tol); anything else
+    # would mean generate() and the step-by-step path disagree.
+    assert div is None or not same_at[div], (div, same_at)
 
 
 @pytest.mark.parametrize("name,kw", [("fused", dict(fused=True)), ("compat", dict(fused=False))])
