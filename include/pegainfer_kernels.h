@@ -154,7 +154,9 @@ int paged_attention_decode_split_kv_cuda(
 
 /* ---- sampling: ffi.rs:98-108; csrc/argmax.cu, csrc/flashinfer_top1.cu --------
  * Both pick the LOWEST index among equal maxima (the reference's radix top-1 leaves
- * tie order undefined).  row_states_scratch: >= 4 KiB (the reference passes 1 MiB). */
+ * tie order undefined).  row_states_scratch: >= 4 KiB (the reference passes 1 MiB).
+ * flashinfer_top1_cuda also leaves the winner's bf16 VALUE in top1_value_scratch[0] on every path (the reference uses it
+ * as scratch only): the vocab-sharded tensor-parallel greedy token compares it across ranks (pk_tp_top1_exchange). */
 void argmax_cuda(const pk_bf16* x, int* out, int n, pk_stream stream);
 void flashinfer_top1_cuda(const pk_bf16* logits, pk_bf16* top1_value_scratch,
                           uint8_t* row_states_scratch, int* output, int vocab_size,
@@ -284,16 +286,26 @@ int pk_b200_decode_attention_fused(
     int chunk_tokens, int max_chunks, int num_qo_heads, int num_kv_heads, int head_dim,
     int page_size, int batch_size, int64_t stride_page, float sm_scale, pk_stream stream);
 
-/* Causal GQA prefill attention over the paged cache on tcgen05/TMEM (prefill_attention_tc.cu): the kernel behind
- * batch_prefill_paged_cuda* when PK_PREFILL_ATTN=tc, callable directly.  Same inputs as the ABI entry minus the
- * FlashInfer tile plan (tiles are derived from q_indptr on the device).  K/V pages are fetched with 4-D TMA tile
- * loads, so the pool base + offsets must be 16-byte aligned.  Returns 0 / cudaError / -1 for unsupported shapes
- * (head_dim != 128, page_size != 16). */
+/* Causal GQA prefill attention over the paged cache on tcgen05/TMEM, callable directly: the kernels behind
+ * batch_prefill_paged_cuda* (replaces csrc/prefill_attention.cu:24-386 / FlashInfer BatchPrefillWithPagedKVCache).
+ * PK_PREFILL_ATTN (read per call) selects tc2 (default; prefill_attention_tc2.cu: two 128-token query tiles per CTA in
+ * ping-pong, O accumulated in TMEM, P handed to the tensor core through TMEM, correction warpgroup), tc
+ * (prefill_attention_tc.cu: one tile per CTA, O in registers) or, for the ABI entry only, legacy (mma.sync).
+ * Same inputs as the ABI entry minus the FlashInfer tile plan (tiles are derived from q_indptr on the device).  K/V
+ * pages are fetched with 4-D TMA tile loads, so the pool base + offsets must be 16-byte aligned.  Returns
+ * 0 / cudaError / -1 for unsupported shapes (head_dim != 128, page_size != 16). */
 int pk_b200_prefill_attention_tc(const pk_bf16* q, pk_bf16* output, const pk_bf16* kv_data, int64_t k_offset_elems,
                                  int64_t v_offset_elems, const int* page_indices, const int* page_indptr,
                                  const int* last_page_len_d, const int* q_indptr, int num_qo_heads, int num_kv_heads,
                                  int head_dim, int page_size, int seq_len, int batch_size, int64_t stride_page,
                                  float sm_scale, pk_stream stream);
+
+/* Measurement aid of prefill_attention_tc2.cu: with PK_FA2_DBG=32 the heaviest CTA of head 0 stamps %clock64 at the
+ * hand-over points of its tile 0; this copies the stamps ([role: softmax, MMA issuer, correction][block < 128][8] u64) to
+ * the host (tools/fa2_trace.py, profiles/r2_prefill_attention.md).  The other PK_FA2_DBG bits (1 no P V MMAs, 2 no S
+ * MMAs, 4 no exponentials, 8 no O rescale, 64 skip one TMEM read, 128 no tile stagger) are timing ablations and give
+ * wrong results by construction; unset = the product path.  Returns cudaError. */
+int pk_b200_fa2_trace_copy(void* host_out, int bytes);
 
 /* pk_b200_decode_attention_fused plus an L2 prefetch of weights that FOLLOWING launches will stream.
  * bs-1 decode attention is latency-bound (a few MB of K/V against ~10 us of dependent steps) and leaves HBM

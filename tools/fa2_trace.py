@@ -37,7 +37,6 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = np.zeros(3 * 128 * 8, dtype=np.uint64)
 f = raw.pk_b200_fa2_trace_copy
-f.argtypes = [C.c_void_p, C.c_int]
 assert f(buf.ctypes.data, buf.nbytes) == 0
 t = buf.reshape(3, 128, 8).astype(np.int64)
 base = t[0, 0, 0]
