@@ -340,9 +340,8 @@ def run_ours(args, cfg, rank, world, dist):
         raise SystemExit(f"prompt {prompt_len} + steps exceed the reference's 4096-position RoPE table")
     pages = 3 * (ctx_max // 16 + 2) + 8
     tp_comm = make_tp_comm(rank, world, dist, max_tokens=256, hidden=cfg.hidden_size) if world > 1 else None
-    persistent = world == 1 and os.environ.get("PK_DECODE", "fused") == "persistent"
     rt = ModelRuntimeConfig(enable_cuda_graph=True, tensor_parallel=TensorParallelConfig(rank, world),
-                            device_ordinal=local_rank, fused=True, persistent=persistent, num_pages=pages,
+                            device_ordinal=local_rank, fused=True, num_pages=pages,
                             max_batch=1, enable_pdl=True)
     t0 = time.perf_counter()
     # ---- checkpoint: generated on the CPU (rank 0), the one the oracle fixtures were computed on ----
@@ -481,7 +480,7 @@ def run_ours(args, cfg, rank, world, dist):
                            "tp_collective": (os.environ.get("PK_TP_MODE", "ll") + " (GEMV-fused LL all-reduce over NVLink peer memory)") if world > 1 else None,
                            "checkpoint": "random-init N(0, 0.02), seed 0, generated on the CPU (the oracle fixtures' checkpoint)"
                            if not on_gpu else "random-init N(0, 0.02), seed 0, CUDA generator (tuning run: NOT the fixtures' checkpoint)",
-                           "decode_impl": "persistent single-launch step" if persistent else "fused multi-kernel graph",
+                           "decode_impl": "fused multi-kernel graph",
                            "launches_per_step": launches_per_step, "model_load_s": round(load_s, 1)},
                 "ttft_ms": ttft_ms, "ttft_prompt_len": prompt_len,
                 "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "tok/s", "ms_per_step": e2e_ms / K,

@@ -244,35 +244,6 @@ int pk_b200_gemv_fused(const pk_b200_gemv_args* args, pk_stream stream);
  * PK_GEMV_KC or the built-in tuning. */
 void pk_b200_set_gemv_tuning(int stages, int ctas_per_sm, int segment_elems);
 
-/* One decode token (bs = 1, TP = 1) in ONE persistent cooperative launch: embedding row, 36 x {qkv GEMV
- * [add+RMSNorm prologue], QK-norm + RoPE + KV append + split-KV attention + merge, o GEMV, gate_up GEMV
- * [add+RMSNorm prologue, SwiGLU epilogue], down GEMV}, lm_head GEMV [final add+RMSNorm] and the greedy
- * arg-max.  A producer warp per SM streams every weight byte of the token through a shared-memory ring
- * with TMA bulk copies and keeps prefetching across the grid barriers that separate the phases.
- * Requires num_q_heads == 4 * num_kv_heads, head_dim 128, page_size 16, hidden_size <= 6144.
- * `layers_dev`: DEVICE array of num_layers pk_b200_layer_ptrs.  `sync_scratch`: >= 4 KiB, zeroed once.
- * `attn_partial`: >= attn_max_chunks * num_q_heads * 130 floats; `attn_counters`: num_kv_heads zeroed ints. */
-typedef struct {
-  const pk_bf16 *qkv, *o, *gate_up, *down, *in_ln, *post_ln, *q_norm, *k_norm;
-} pk_b200_layer_ptrs;
-typedef struct {
-  const void* layers_dev;
-  int num_layers, hidden_size, intermediate_size, vocab_size, num_q_heads, num_kv_heads, head_dim, page_size;
-  float rms_eps, sm_scale;
-  const pk_bf16 *embed, *lm_head, *final_norm, *cos_cache, *sin_cache, *zero_residual;
-  const uint32_t* token_ids;
-  const int *positions, *page_indices, *page_indptr, *last_page_len;
-  pk_bf16* kv_data;
-  int64_t layer_stride, kv_block_len, stride_page;
-  pk_bf16 *hidden_a, *hidden_b, *q, *k, *v, *attn_out, *attn_proj, *mlp_act, *mlp_out, *logits;
-  float* attn_partial;
-  int* attn_counters;
-  int attn_max_chunks;
-  void* sync_scratch;
-  int* sample_out;
-} pk_b200_decode_step_args;
-int pk_b200_decode_step_persistent(const pk_b200_decode_step_args* args, pk_stream stream);
-
 /* QK-norm + RoPE + KV append + split-KV GQA decode attention + merge in ONE launch.
  * q/k/v are the raw projections of the step ([dim, bs]); k is normed/roped and both k, v
  * are appended at `positions` before use.  partial_* : fp32 scratch

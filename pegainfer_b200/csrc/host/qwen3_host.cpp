@@ -32,7 +32,7 @@ std::string KernelLib::load(const std::string& p) {
   PQ_REQ(paged_attention_decode_cuda) PQ_REQ(paged_attention_decode_split_kv_cuda)
   PQ_REQ(flashinfer_top1_cuda)
   PQ_OPT(pk_b200_launch_count) PQ_OPT(pk_b200_set_pdl) PQ_OPT(pk_b200_gemv_fused) PQ_OPT(pk_b200_gemm_segments)
-  PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_b200_decode_step_persistent) PQ_OPT(pk_tp_all_reduce_rows)
+  PQ_OPT(pk_b200_decode_attention_fused) PQ_OPT(pk_tp_all_reduce_rows)
   PQ_OPT(pk_tp_all_reduce_add_rms_norm) PQ_OPT(pk_tp_max_rows)
   PQ_OPT(pk_b200_decode_attention_fused_prefetch) PQ_OPT(pk_b200_gemv_grid) PQ_OPT(pk_tp_top1_exchange) PQ_OPT(pk_b200_gemm_swiglu)
 #undef PQ_REQ
@@ -265,8 +265,6 @@ struct Qwen3Model {
   bool decode_kernels_wide(int bs);
   bool unified_step(int n_prefill, const uint32_t* prompt_tokens, const int* lens, const int* prefill_kv_ids, int n_decode,
                     const uint32_t* decode_tokens, const int* decode_kv_ids, void** prefill_logits, void** decode_logits);
-  bool decode_kernels_persistent();
-  DeviceBuf layer_ptrs_d, sync_scratch;
   HiddenStates pf_hid, pf_hid_out, pf_nrm, pf_q, pf_k, pf_v, pf_o, pf_gu, pf_act, pf_att;
   DeviceBuf pf_plan;
   std::vector<int> plan_pack;
@@ -484,21 +482,6 @@ bool Qwen3Model::create_decode_buffers() {
   ok = ok && sample_out.alloc_zeros(64 * 4) && top1_val.alloc_zeros(256) && top1_states.alloc_zeros(1 << 20) &&
        cudaMallocHost((void**)&sample_h, 64 * 4) == cudaSuccess;
   if (!ok) return fail(std::string("decode buffer allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
-  if (rt.mode == 2) {  // persistent decode: device table of per-layer weight pointers + sync scratch
-    std::vector<pk_b200_layer_ptrs> lp(c.num_hidden_layers);
-    for (int i = 0; i < c.num_hidden_layers; ++i) {
-      TransformerBlock& L = layers[i];
-      lp[i] = pk_b200_layer_ptrs{L.attention.qkv_proj.data.bf(), L.attention.o_proj.data.bf(),
-                                 L.mlp.gate_up_proj.data.bf(), L.mlp.down_proj.data.bf(),
-                                 L.input_layernorm.data.bf(), L.post_attention_layernorm.data.bf(),
-                                 L.attention.q_norm.data.bf(), L.attention.k_norm.data.bf()};
-    }
-    if (!layer_ptrs_d.alloc_zeros(lp.size() * sizeof(pk_b200_layer_ptrs)) || !sync_scratch.alloc_zeros(8192))
-      return fail("persistent decode scratch allocation failed");
-    if (!cu(cudaMemcpy(layer_ptrs_d.ptr, lp.data(), lp.size() * sizeof(pk_b200_layer_ptrs), cudaMemcpyHostToDevice),
-            "layer pointer upload"))
-      return false;
-  }
   return true;
 }
 
@@ -1040,35 +1023,6 @@ bool Qwen3Model::decode_kernels_wide(int bs) {
   return true;
 }
 
-// mode 2: the whole token in one cooperative launch (decode_persistent.cu)
-bool Qwen3Model::decode_kernels_persistent() {
-  const Config& c = config;
-  if (!layer_ptrs_d.ptr) return fail("persistent decode buffers were not created");
-  const int* M = meta_d.i32();
-  pk_b200_decode_step_args g{};
-  g.layers_dev = layer_ptrs_d.ptr;
-  g.num_layers = c.num_hidden_layers; g.hidden_size = c.hidden_size; g.intermediate_size = local_inter();
-  g.vocab_size = c.vocab_size; g.num_q_heads = local_heads(); g.num_kv_heads = local_kv_heads();
-  g.head_dim = c.head_dim; g.page_size = kPageSize;
-  g.rms_eps = c.rms_norm_eps; g.sm_scale = 1.0f / sqrtf((float)c.head_dim);
-  g.embed = embed_tokens.data.bf(); g.lm_head = output_projection_full().data.bf(); g.final_norm = norm.data.bf();
-  g.cos_cache = cos_cache.data.bf(); g.sin_cache = sin_cache.data.bf(); g.zero_residual = zero_residual.bf();
-  g.token_ids = reinterpret_cast<const uint32_t*>(M + mo.token_ids);
-  g.positions = M + mo.positions; g.page_indices = M + mo.page_indices; g.page_indptr = M + mo.page_indptr;
-  g.last_page_len = M + mo.last_page_len;
-  g.kv_data = kv_buffer.bf(); g.layer_stride = layout.layer_stride; g.kv_block_len = layout.kv_block_len;
-  g.stride_page = layout.page_stride;
-  g.hidden_a = hidden.data.bf(); g.hidden_b = hidden_b.data.bf(); g.q = q.data.bf(); g.k = kbuf.data.bf();
-  g.v = v.data.bf(); g.attn_out = attn_out.data.bf(); g.attn_proj = attn_proj.data.bf();
-  g.mlp_act = mlp_act.data.bf(); g.mlp_out = mlp_out.data.bf(); g.logits = logits.data.bf();
-  g.attn_partial = static_cast<float*>(attn_partial.ptr); g.attn_counters = attn_counters.i32();
-  g.attn_max_chunks = attn_max_chunks;
-  g.sync_scratch = sync_scratch.ptr; g.sample_out = sample_out.i32();
-  const int rc = k.pk_b200_decode_step_persistent(&g, ctx.stream);
-  if (rc != 0) return fail("pk_b200_decode_step_persistent failed (rc " + std::to_string(rc) + ")");
-  return true;
-}
-
 // Advance the KV states by one token and write the step's packed metadata block into `mh`
 // (batch_decode.rs:26-59 + sync_paged_meta / sync_split_kv_meta of batch_decode_buffers.rs:177-279).
 bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, const int* kv_ids, int* mh,
@@ -1151,15 +1105,12 @@ bool Qwen3Model::build_step_meta(int bs, int padded, const uint32_t* tokens, con
 bool Qwen3Model::run_step_kernels(int padded, bool split) {
   const bool fused = rt.mode >= 1;
   cudaStream_t st = ctx.stream;
-  const bool persistent = rt.mode == 2 && padded == 1 && !tp.is_sharded() && k.pk_b200_decode_step_persistent &&
-                          local_heads() == 4 * local_kv_heads() && config.hidden_size <= 6144;
   auto body = [&]() {
-    if (persistent) return decode_kernels_persistent();
     if (fused && padded > 4) return decode_kernels_wide(padded);
     return fused ? decode_kernels_fused(padded) : decode_kernels_compat(padded, split);
   };
   if (!rt.enable_cuda_graph) return body();
-  const int key = padded * 4 + (persistent ? 3 : (fused ? 2 : (split ? 1 : 0)));
+  const int key = padded * 4 + (fused ? 2 : (split ? 1 : 0));
   auto& g = graphs[key];
   if (!g) g.reset(new CudaGraphState());
   if (!g->captured()) {
@@ -1459,7 +1410,6 @@ __attribute__((visibility("default"))) void* pq_debug_buffer(void* mp, const cha
   if (n == "logits") return m->logits.data.ptr;
   if (n == "kv") return m->kv_buffer.ptr;
   if (n == "attn_out") return m->attn_out.data.ptr;
-  if (n == "persist_dbg") return m->sync_scratch.ptr ? static_cast<char*>(m->sync_scratch.ptr) + 4096 : nullptr;
   return nullptr;
 }
 

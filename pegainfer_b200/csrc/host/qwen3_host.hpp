@@ -41,7 +41,7 @@ struct KernelLib {
   PQ_FN(flashinfer_top1_cuda)
   // B200 extensions (null when driving the reference's kernels)
   PQ_FN(pk_b200_launch_count) PQ_FN(pk_b200_set_pdl) PQ_FN(pk_b200_gemv_fused) PQ_FN(pk_b200_gemm_segments)
-  PQ_FN(pk_b200_decode_attention_fused) PQ_FN(pk_b200_decode_step_persistent) PQ_FN(pk_tp_all_reduce_rows)
+  PQ_FN(pk_b200_decode_attention_fused) PQ_FN(pk_tp_all_reduce_rows)
   PQ_FN(pk_tp_all_reduce_add_rms_norm) PQ_FN(pk_tp_max_rows)
   PQ_FN(pk_b200_decode_attention_fused_prefetch) PQ_FN(pk_b200_gemv_grid) PQ_FN(pk_tp_top1_exchange) PQ_FN(pk_b200_gemm_swiglu)
 #undef PQ_FN
@@ -156,8 +156,7 @@ struct RuntimeConfig {
   int device_ordinal = 0;
   int tp_rank = 0, tp_world = 1;
   int enable_cuda_graph = 1;
-  int mode = 1;        // 0: reference op sequence through the ffi.rs ABI only; 1: fused B200 path;
-                       // 2: fused + the single-launch persistent decode step for bs == 1, TP == 1
+  int mode = 1;        // 0: reference op sequence through the ffi.rs ABI only; 1: fused B200 path
   int num_pages = 0;   // 0: 85 % of free memory (weights.rs:309-334), capped
   int max_batch = 4;
   int enable_pdl = 1;

@@ -86,7 +86,6 @@ EXT_SIGNATURES = {
     "pk_b200_gemm_segments": (i32, [vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
     "pk_b200_gemv_fused": (i32, [C.POINTER(GemvArgs), vp]),
     "pk_b200_set_gemv_tuning": (None, [i32, i32, i32]),
-    "pk_b200_decode_step_persistent": (i32, [vp, vp]),
     "pk_b200_decode_attention_fused": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7 + [i64, f32, vp]),
     "pk_b200_decode_attention_fused_prefetch": (i32, [vp, vp, vp, vp, vp, i64, i64] + [vp] * 8 + [f32, vp, vp] + [i32] * 7
                                                 + [i64, f32, C.POINTER(PrefetchSpan), i32, vp]),

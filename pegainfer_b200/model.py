@@ -90,7 +90,6 @@ class ModelRuntimeConfig:
     tensor_parallel: TensorParallelConfig = TensorParallelConfig()
     device_ordinal: int = 0
     fused: bool = True          # False: the reference's op sequence through the ffi.rs ABI only
-    persistent: bool = False    # fused + single-launch persistent decode step (bs 1, TP 1)
     num_pages: int = 0          # 0: 85 % of free memory
     max_batch: int = 4
     enable_pdl: bool = True
@@ -126,7 +125,7 @@ class Qwen3Model:
                        cfg.num_key_value_heads, cfg.head_dim, cfg.vocab_size, cfg.rms_norm_eps, cfg.rope_theta,
                        int(cfg.tie_word_embeddings))
         pr = _PqRuntime(rt.device_ordinal, rt.tensor_parallel.rank, rt.tensor_parallel.world_size,
-                        int(rt.enable_cuda_graph), (2 if rt.persistent else 1) if rt.fused else 0, rt.num_pages, rt.max_batch,
+                        int(rt.enable_cuda_graph), 1 if rt.fused else 0, rt.num_pages, rt.max_batch,
                         int(rt.enable_pdl))
         lib_path = rt.kernel_lib or ffi.KERNEL_LIB_PATH
         torch.cuda.set_device(rt.device_ordinal)

@@ -21,8 +21,7 @@ pytestmark = pytest.mark.gpu
 REF_LIB = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libkernels_ref.so"))
 TOL_ULP = 6  # logits, in bf16 ulps at the row's max |logit| (tiny/small configs, <= 4 layers)
 
-VARIANTS = [("fused", dict(fused=True)), ("persistent", dict(fused=True, persistent=True)),
-            ("persistent-nograph", dict(fused=True, persistent=True, enable_cuda_graph=False)),
+VARIANTS = [("fused", dict(fused=True)), ("fused-nograph", dict(fused=True, enable_cuda_graph=False)),
             ("compat", dict(fused=False)),
             ("compat-nograph", dict(fused=False, enable_cuda_graph=False))]
 if os.path.exists(REF_LIB):

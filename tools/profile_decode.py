@@ -13,9 +13,8 @@ from pegainfer_b200.synthetic import iter_random_weights, synthetic_prompt  # no
 ctx = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pdl = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
-persistent = bool(int(sys.argv[4])) if len(sys.argv) > 4 else False
 m = Qwen3Model(QWEN3_4B, iter_random_weights(QWEN3_4B, 0, "cuda"),
-               ModelRuntimeConfig(enable_cuda_graph=False, num_pages=ctx // 16 + 64, max_batch=1, enable_pdl=pdl, persistent=persistent))
+               ModelRuntimeConfig(enable_cuda_graph=False, num_pages=ctx // 16 + 64, max_batch=1, enable_pdl=pdl))
 kv = m.alloc_kv()
 tok = m.sample_greedy(m.prefill([synthetic_prompt(ctx)], [kv])[0])
 torch.cuda.synchronize()

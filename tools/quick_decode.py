@@ -24,7 +24,7 @@ a = ap.parse_args()
 cfg = PRESETS[a.model]
 pages = 3 * ((a.prompt + a.reps * a.steps + 128) // 16 + 2) + 8
 rt = ModelRuntimeConfig(enable_cuda_graph=True, tensor_parallel=TensorParallelConfig(0, 1), device_ordinal=0, fused=True,
-                        persistent=False, num_pages=pages, max_batch=1, enable_pdl=True,
+                        num_pages=pages, max_batch=1, enable_pdl=True,
                         kernel_lib=os.path.abspath(a.lib) if a.lib else None)
 model = Qwen3Model(cfg, iter_random_weights(cfg, seed=0, device="cuda"), rt)
 prompt = synthetic_prompt(a.prompt)
