@@ -16,9 +16,13 @@ pdl = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 m = Qwen3Model(QWEN3_4B, iter_random_weights(QWEN3_4B, 0, "cuda"),
                ModelRuntimeConfig(enable_cuda_graph=False, num_pages=ctx // 16 + 64, max_batch=1, enable_pdl=pdl))
 kv = m.alloc_kv()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # with `ncu --profile-from-start off` the weight generation stays out of the launch list
 tok = m.sample_greedy(m.prefill([synthetic_prompt(ctx)], [kv])[0])
 torch.cuda.synchronize()
 for _ in range(steps):
     _, s = m.decode([tok], [kv], want_logits=False)
     tok = s[0]
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done", tok)
