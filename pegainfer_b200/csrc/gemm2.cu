@@ -347,11 +347,15 @@ int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
     }
   }
   if (!swiglu) {  // is the single-CTA kernel (gemm.cu: 128-token tiles of width 256 / 160 / 128 on every SM) strictly better?
+    // One cost unit of the single-CTA kernel takes 1.75-2.3 x as long as one of the pair kernel (it is bound by its own
+    // shared-memory port, see the header): at 2048 tokens o_proj 80.8 us (2 waves of 160-wide tiles, 384 units) vs 46.5 us
+    // for the pair's one wave of 320-wide tiles (458 units), down_proj 173 vs 88 us (profiles/README.md round 2).  Without
+    // the factor the model sent both back to the single-CTA kernel (r2_v3_prefill_decode_launches.csv: 2 x 89 us per layer).
     const long m1 = (N + G2_BM - 1) / G2_BM;
     const int w1[3] = {256, 160, 128};
     for (int i = 0; i < 3; ++i) {
       const long waves = (m1 * ((M + w1[i] - 1) / w1[i]) + sm_count() - 1) / sm_count();
-      if (waves * (w1[i] + 32) < best_cost) return -2;
+      if (waves * (w1[i] + 32) * 7 / 4 < best_cost) return -2;
     }
   }
   const int rows_w = swiglu ? 2 * M : M;
