@@ -649,7 +649,11 @@ def test_prefill_attention_tc(starts, lens, nq, nkv, impl, monkeypatch):
     from tests.helpers import ulp_err
     e = ulp_err(bits(out).ravel(), np.asarray(want).ravel(), float(np.abs(f32(want)).max()) / 32)
     print(f"\n[prefill attention {impl}] lens {lens} starts {starts}: max err {e.max():.2f} ulp, {float((e == 0).mean()):.4f} bit-exact")
-    assert_bf16_close(bits(out), want, 8, floor=float(np.abs(f32(want)).max()) / 32, what="tc prefill attn")
+    # Measured on B200 (profiles/r2_prefill_attention_parity.txt): 1.1-2.5 ulp on every case but the one whose chunk starts
+    # 900 tokens into the request (6.7 ulp): there the kernels' 128-token blocks and the oracle's 64-token tiles advance the
+    # running maximum at different KV positions over a long cached prefix, so more P values round differently.
+    tol = 8 if max(starts) >= 512 else 4
+    assert_bf16_close(bits(out), want, tol, floor=float(np.abs(f32(want)).max()) / 32, what="tc prefill attn")
     assert lib.pk_b200_prefill_attention_tc(p(dev(q)), p(out), p(dev(pg.kv)), L.k_offset(layer), L.v_offset(layer),
                                             p(i32(pg.pi)), p(i32(pg.ip)), p(i32(pg.lpl)), p(i32(q_indptr)), nq, nkv, hd, 32,
                                             T, bs, L.page_stride, sm, stream()) == -1  # page size 32: unsupported
