@@ -254,10 +254,14 @@ def cpu_arm_ctx(world):
 
 def cpu_sample_text(cfg, n, runs, threads, ctx_end):
     spread = (max(runs) - min(runs)) / statistics.median(runs)
+    try:
+        load = f"; host load average {os.getloadavg()[0]:.0f} (shared host: other tenants' threads slow the bound team)"
+    except OSError:
+        load = ""
     return (f"{len(runs)} x {n} full-depth {cfg.name} greedy decode steps of the CPU oracle ending at ctx {ctx_end} (context "
             f"pre-filled, no CPU prefill), bs 1; OpenMP {threads} threads (OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, "
             f"OMP_PLACES={os.environ.get('OMP_PLACES')}), weights first-touched per thread; runs "
-            f"{[round(r, 2) for r in runs]} tok/s, spread {spread:.1%}")
+            f"{[round(r, 2) for r in runs]} tok/s, spread {spread:.1%}{load}")
 
 
 def run_reference(args, cfg, rank, world):
