@@ -180,6 +180,8 @@ def _cpu_decode_rate_here(cfg, weights_np, ctx, budget_s, repeats, threads):
     t_w = time.perf_counter()
     tok = O.argmax(orc.decode([tok], [kv])[0])
     t_step = time.perf_counter() - t_w
+    if t_step * 2 * repeats > 2 * budget_s:  # pathologically slow here (see cpu_decode_rate): one sample, no timed loop
+        return 1.0 / t_step, [1.0 / t_step], 1, threads, kv.seq_len
     n = max(2, min(16, int(budget_s / repeats / max(t_step, 1e-3))))
     runs = []
     for _ in range(repeats):
@@ -206,22 +208,13 @@ def _cpu_arm_child(argv):
     print("CPU_ARM_RESULT " + json.dumps({"rate": rate, "runs": runs, "n": n, "threads": thr, "ctx_end": ctx_end}), flush=True)
 
 
-def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
-    """Greedy decode steps of the CPU oracle at context `ctx` (the GPU arm's), all host threads.
-
-    The context is created with OracleQwen3.fill_context (random K/V, no 2048-token CPU prefill: decode timing does
-    not depend on the cached values); weights are re-homed for NUMA locality (rehome_weights); the OpenMP team size
-    is set explicitly and read back.  `repeats` timed runs of n steps each -> (median tok/s, runs, n, threads).
-    Runs in a child process (see _cpu_arm_child; the checkpoint travels as .npy files in /dev/shm); if that fails for
-    any reason the same loop runs in this process."""
-    threads = host_threads()
+def _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads):
     import shutil
     import tempfile
     import numpy as np
-    tmp = None
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="pk_cpu_arm_", dir=base)
     try:
-        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-        tmp = tempfile.mkdtemp(prefix="pk_cpu_arm_", dir=base)
         names = list(weights_np.keys())
         for i, name in enumerate(names):
             np.save(os.path.join(tmp, f"{i}.npy"), np.ascontiguousarray(weights_np[name]))
@@ -231,21 +224,48 @@ def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-arm-child", tmp, cfg.name, str(ctx), str(budget_s),
-                            str(repeats), str(threads)], env=env, capture_output=True, text=True, timeout=budget_s * 6 + 240)
+                            str(repeats), str(threads)], env=env, capture_output=True, text=True, timeout=budget_s * 4 + 180)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("CPU_ARM_RESULT ")]
         if r.returncode != 0 or not line:
             raise RuntimeError(f"cpu arm child failed (rc {r.returncode}): {r.stderr[-300:]}")
         d = json.loads(line[-1][len("CPU_ARM_RESULT "):])
-        os.environ.setdefault("OMP_PROC_BIND", "close")   # what the child ran with (cpu_sample_text reports these)
-        os.environ.setdefault("OMP_PLACES", "threads")
         return d["rate"], d["runs"], d["n"], d["threads"], d["ctx_end"]
-    except Exception as e:
-        print(f"[bench] cpu arm child unavailable ({type(e).__name__}: {e}); timing in-process", file=sys.stderr)
-        _pin_openmp()
-        return _cpu_decode_rate_here(cfg, weights_np, ctx, budget_s, repeats, threads)
     finally:
-        if tmp:
-            shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+_CPU_ARM_NOTE = ""
+
+
+def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
+    """Greedy decode steps of the CPU oracle at context `ctx` (the GPU arm's), all host threads.
+
+    The context is created with OracleQwen3.fill_context (random K/V, no 2048-token CPU prefill: decode timing does
+    not depend on the cached values); weights are re-homed for NUMA locality (rehome_weights); the OpenMP team size
+    is set explicitly and read back.  `repeats` timed runs of n steps each -> (median tok/s, runs, n, threads).
+
+    Where the loop runs matters on the 128-thread GPU hosts, for reasons we could not pin down before the round's GPU
+    time ran out (same box, same loop, bound threads in every case): inside the GPU arm's process 2.7-2.9 tok/s; inside
+    a fresh `--impl reference` process 0.03-0.06; in a child process that imports numpy + the oracle only 0.33-0.38;
+    unbound threads: no step within 170 s.  So BOTH placements are timed, each bounded, and the better one is the
+    baseline (the CPU gets its best showing); `sample` names both."""
+    global _CPU_ARM_NOTE
+    threads = host_threads()
+    results = []
+    try:
+        results.append(("child process (numpy + oracle only)", _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads)))
+    except Exception as e:
+        print(f"[bench] cpu arm child unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+    try:
+        _pin_openmp()
+        results.append(("this process", _cpu_decode_rate_here(cfg, weights_np, ctx, budget_s, repeats, threads)))
+    except Exception as e:
+        if not results:
+            raise
+        print(f"[bench] in-process cpu arm failed ({type(e).__name__}: {e})", file=sys.stderr)
+    best = max(results, key=lambda r: r[1][0])
+    _CPU_ARM_NOTE = "; placements timed: " + ", ".join(f"{name} {res[0]:.2f} tok/s" for name, res in results) + f" -> reported: {best[0]}"
+    return best[1]
 
 
 def cpu_arm_ctx(world):
@@ -261,7 +281,7 @@ def cpu_sample_text(cfg, n, runs, threads, ctx_end):
     return (f"{len(runs)} x {n} full-depth {cfg.name} greedy decode steps of the CPU oracle ending at ctx {ctx_end} (context "
             f"pre-filled, no CPU prefill), bs 1; OpenMP {threads} threads (OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, "
             f"OMP_PLACES={os.environ.get('OMP_PLACES')}), weights first-touched per thread; runs "
-            f"{[round(r, 2) for r in runs]} tok/s, spread {spread:.1%}{load}")
+            f"{[round(r, 2) for r in runs]} tok/s, spread {spread:.1%}{load}{_CPU_ARM_NOTE}")
 
 
 def run_reference(args, cfg, rank, world):
