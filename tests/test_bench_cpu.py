@@ -43,3 +43,5 @@ def test_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] >= 1 and len(line["cpu_baseline"]["runs"]) == 3
     assert "OpenMP" in line["cpu_baseline"]["sample"] and "ctx" in line["cpu_baseline"]["sample"]
+    # both placements of the timed loop are tried (a child process without torch, and this process) and named
+    assert "child process" in line["cpu_baseline"]["sample"] and "this process" in line["cpu_baseline"]["sample"]
