@@ -537,7 +537,11 @@ def run_ours(args, cfg, rank, world, dist):
         if not args.no_gpu_reference:
             gpu_ref = gpu_reference_leg(cfg, keep_cpu, prompt, pages)
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline_leg(cfg, keep_cpu)
+            try:
+                cpu = cpu_baseline_leg(cfg, keep_cpu)
+            except Exception as e:  # a baseline leg must never take the benchmark line down
+                cpu = {"value": None, "unit": "tok/s", "cores": host_threads(), "kind": "port",
+                       "sample": f"unavailable: {type(e).__name__}: {e}"[:300]}
         keep_cpu = None
         if not args.no_tp_base:
             tp_base = tp_base_leg(PRESETS["qwen3-8b"], local_rank)
