@@ -19,7 +19,8 @@ def test_cpu_decode_rate_at_the_gpu_arms_context():
     w = to_numpy_bits(random_weights(cfg, seed=0, device="cpu"))
     rate, runs, n, threads, ctx_end = bench.cpu_decode_rate(cfg, w, 2048, budget_s=3.0)
     assert rate > 0 and len(runs) == 3 and n >= 2 and threads >= 1
-    assert ctx_end == 2048 + 2 + 3 * n  # warm-up step + calibration step + the timed steps, all past the filled context
+    # first-touch step + the untimed steps until the step time is steady (1..64) + the timed steps, all past the filled context
+    assert 2048 + 2 + 3 * n <= ctx_end <= 2048 + 1 + 64 + 3 * n
 
 
 def test_oracle_thread_control_and_row_spreading():
