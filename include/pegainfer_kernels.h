@@ -192,6 +192,11 @@ int pk_b200_gemm_segments(const pk_bf16* W, const pk_bf16* X, pk_bf16* const* Y,
  * Y[tok][M] = bf16(silu(bf16(gate.x)) * bf16(up.x)) -- gemm_cuda + silu_mul_fused_cuda with the same rounding points.
  * Returns 0, or -2 when the shape is not for this kernel (run the two-kernel sequence instead). */
 int pk_b200_gemm_swiglu(const pk_bf16* W, const pk_bf16* X, pk_bf16* Y, int M, int N, int K, pk_stream stream);
+/* Which prefill GEMM kernel a [M features] x [N tokens] x [K] problem gets on a GPU with `sms` SMs (the choice gemm_cuda /
+ * pk_b200_gemm_segments / pk_b200_gemm_swiglu make internally): 256 / 320 / 128 = tile width of the CTA-pair tcgen05 kernel
+ * (gemm2.cu), -2 = the single-CTA kernel (gemm.cu, split-K when skinny).  Pure host arithmetic, no CUDA call: the wave-count
+ * cost model calibrated on B200 measurements (profiles/README.md round 2) is pinned by a CPU test. */
+int pk_b200_gemm_plan(int M, int N, int K, int swiglu, int sms);
 
 /* GEMV with fused prologue/epilogue for decode (N == 1..4 tokens), one launch:
  *   x_mode 0: x = X as is ([N, K]).

@@ -318,29 +318,25 @@ cudaError_t g2_launch(const CUtensorMap& mx, const CUtensorMap& mw, const G2Args
 
 }  // namespace
 
-// Returns 0 when launched, -2 when the shape / alignment is not for this kernel (caller uses the 1-CTA kernel).
-int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K, int swiglu,
-                     cudaStream_t stream) {
-  if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(W) & 15) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return -2;
+// Tile choice by wave count (cost ~ waves x (tile width + epilogue)), in the units of gemm.cu's model: a pair tile of 256
+// tokens on sms/2 pairs costs what a 128-token tile of the same width costs on sms single CTAs.  Returns the candidate
+// index (0: 256-wide, 1: 2 x 160-wide, 2: 128-wide) or -2 when the single-CTA kernel of gemm.cu should take the shape.
+// Pure host arithmetic (exported as pk_b200_gemm_plan so the calibration is pinned by a CPU test).
+static int g2_plan(int M, int N, int K, int swiglu, int sms) {
+  if (K % 8 != 0 || M <= 0 || sms < 2) return -2;
   if (N <= G2_BM) return -2;  // one token tile: nothing for the second CTA of a pair to do
-  G2Args a{Y, Y1, Y2, e0, e1, M, N, K, swiglu};
-  CUtensorMap mx, mw;
-  if (!g2_make_map(&mx, X, N, K, G2_BM)) return -2;
-  // Tile choice by wave count (cost ~ waves x (tile width + epilogue)), in the units of gemm.cu's model: a pair tile
-  // of 256 tokens on sms/2 pairs costs what a 128-token tile of the same width costs on sms single CTAs.
-  const int pairs = sm_count() / 2;
+  const int pairs = sms / 2;
   const long m_tiles = (N + 2 * G2_BM - 1) / (2 * G2_BM);
-  struct Cand { int bn, nsub; };
-  const Cand cands[3] = {{256, 1}, {160, 2}, {128, 1}};
+  const int bn[3] = {256, 160, 128}, nsub[3] = {1, 2, 1};
   int best = -1;
   long best_cost = -1;
   for (int ci = 0; ci < (swiglu ? 1 : 3); ++ci) {
-    const int tn = cands[ci].bn * cands[ci].nsub;
-    const long nt = swiglu ? (M + cands[ci].bn / 2 - 1) / (cands[ci].bn / 2) : (M + tn - 1) / tn;
+    const int tn = bn[ci] * nsub[ci];
+    const long nt = swiglu ? (M + bn[ci] / 2 - 1) / (bn[ci] / 2) : (M + tn - 1) / tn;
     const long waves = (m_tiles * nt + pairs - 1) / pairs;
     // a 320-wide tile has ONE accumulator buffer in TMEM: its epilogue is not hidden behind the next tile's MMAs
     // (measured: gate_up 209 us with 320-wide vs 165 us with 256-wide tiles), so it only pays as a single wave
-    const long cost = waves * (cands[ci].nsub == 2 ? tn + tn / 3 + 32 : tn + 32);
+    const long cost = waves * (nsub[ci] == 2 ? tn + tn / 3 + 32 : tn + 32);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = ci;
@@ -354,12 +350,25 @@ int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
     const long m1 = (N + G2_BM - 1) / G2_BM;
     const int w1[3] = {256, 160, 128};
     for (int i = 0; i < 3; ++i) {
-      const long waves = (m1 * ((M + w1[i] - 1) / w1[i]) + sm_count() - 1) / sm_count();
+      const long waves = (m1 * ((M + w1[i] - 1) / w1[i]) + sms - 1) / sms;
       if (waves * (w1[i] + 32) * 7 / 4 < best_cost) return -2;
     }
   }
+  return best;
+}
+
+// Returns 0 when launched, -2 when the shape / alignment is not for this kernel (caller uses the 1-CTA kernel).
+int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, int e0, int e1, int M, int N, int K, int swiglu,
+                     cudaStream_t stream) {
+  if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(W) & 15) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return -2;
+  const int best = g2_plan(M, N, K, swiglu, sm_count());
+  if (best < 0) return -2;
+  G2Args a{Y, Y1, Y2, e0, e1, M, N, K, swiglu};
+  CUtensorMap mx, mw;
+  if (!g2_make_map(&mx, X, N, K, G2_BM)) return -2;
+  const int bn[3] = {256, 160, 128};
   const int rows_w = swiglu ? 2 * M : M;
-  if (!g2_make_map(&mw, W, rows_w, K, cands[best].bn / 2)) return -2;
+  if (!g2_make_map(&mw, W, rows_w, K, bn[best] / 2)) return -2;
   cudaError_t e;
   if (best == 0) e = g2_launch<256, 1, 6>(mx, mw, a, stream);
   else if (best == 1) e = g2_launch<160, 2, 5>(mx, mw, a, stream);
@@ -368,3 +377,11 @@ int launch_gemm_pair(const bf16* W, const bf16* X, bf16* Y, bf16* Y1, bf16* Y2, 
 }
 
 }  // namespace pk
+
+// Which prefill GEMM kernel a [M features] x [N tokens] x [K] problem gets on a GPU with `sms` SMs: 256 / 320 / 128 = tile
+// width of the CTA-pair kernel, -2 = the single-CTA kernel (gemm.cu; split-K when skinny).  No CUDA call.
+extern "C" int pk_b200_gemm_plan(int M, int N, int K, int swiglu, int sms) {
+  const int widths[3] = {256, 320, 128};
+  const int best = pk::g2_plan(M, N, K, swiglu, sms);
+  return best < 0 ? -2 : widths[best];
+}

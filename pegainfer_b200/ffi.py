@@ -92,6 +92,7 @@ EXT_SIGNATURES = {
     "pk_b200_gemv_grid": (i32, [i32, i32]),
     "pk_b200_prefill_attention_tc": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, vp]),
     "pk_b200_fa2_trace_copy": (i32, [vp, i32]),
+    "pk_b200_gemm_plan": (i32, [i32, i32, i32, i32, i32]),
     "pk_tp_flag_bytes": (i64, []),
     "pk_tp_comm_create": (vp, [i32, i32, C.POINTER(vp), C.POINTER(vp), i64]),
     "pk_tp_comm_destroy": (None, [vp]),

@@ -61,3 +61,21 @@ def test_sass_is_blackwell_native(built):
     assert "UTMALDG" in sass, "no TMA tensor load in SASS"
     assert "UBLKCP" in sass, "no cp.async.bulk in SASS"
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
+
+
+def test_prefill_gemm_plan_matches_the_measured_calibration():
+    """pk_b200_gemm_plan (host arithmetic of gemm2.cu, no CUDA call) on a 148-SM GPU: the choices that were measured on B200
+    (profiles/README.md round 2, gpurun_out/c18_prefill_ops.log).  o_proj / down_proj at 2048 tokens must take the pair
+    kernel's one-wave 320-wide tile (46 / 89 us; the single-CTA kernel needs 81 / 173 us) -- a cost-model slip that sent
+    them back to the single-CTA kernel cost 1.4 ms of TTFT(2048) until it was calibrated."""
+    from pegainfer_b200 import ffi
+    plan = ffi.lib().pk_b200_gemm_plan
+    H, I, QKV, Q = 2560, 9728, 6144, 4096  # Qwen3-4B
+    assert plan(Q, 2048, H, 0, 148) == 256 and plan(QKV, 2048, H, 0, 148) == 256   # q / fused qkv
+    assert plan(H, 2048, Q, 0, 148) == 320 and plan(H, 2048, I, 0, 148) == 320       # o_proj, down_proj
+    assert plan(I, 2048, H, 1, 148) == 256                                            # gate_up + SwiGLU: 256-wide only
+    assert plan(2 * I, 2048, H, 0, 148) == 256                                        # plain gate_up: never the single-buffered 320
+    for m, k in ((Q, H), (H, Q), (H, I), (2 * I, H)):
+        assert plan(m, 128, k, 0, 148) == -2                                          # one token tile: single-CTA kernel (split-K)
+    assert plan(I, 128, H, 1, 148) == -2 and plan(Q, 2048, H + 4, 0, 148) == -2       # SwiGLU at 128 tokens, K % 8 != 0
+    assert plan(4096, 2048, 4096, 0, 148) in (256, 320, 128)                          # Qwen3-8B q: some pair tile
