@@ -302,7 +302,7 @@ def run_reference(args, cfg, rank, world):
     t0 = time.perf_counter()
     w = to_numpy_bits(random_weights(cfg, seed=0, device="cpu"))
     gen_s = time.perf_counter() - t0
-    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(world), budget_s=40.0)
+    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(world), budget_s=30.0)
     sample = cpu_sample_text(cfg, n, runs, threads, ctx_end) + f"; weights generated on CPU in {gen_s:.0f}s"
     line = {"impl": "reference", "metric": "decode_tok_s", "value": rate, "unit": "tok/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True,
@@ -615,7 +615,7 @@ def profile_traffic():
 def cpu_baseline_leg(cfg, weights_cpu):
     from pegainfer_b200.synthetic import to_numpy_bits
     w = to_numpy_bits(weights_cpu)
-    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(1), budget_s=24.0)
+    rate, runs, n, threads, ctx_end = cpu_decode_rate(cfg, w, cpu_arm_ctx(1), budget_s=16.0)
     return {"value": rate, "unit": "tok/s", "cores": threads, "kind": "port", "runs": runs,
             "sample": cpu_sample_text(cfg, n, runs, threads, ctx_end)}
 
