@@ -202,6 +202,30 @@ def _cpu_decode_rate_here(cfg, weights_np, ctx, budget_s, repeats, threads):
     return statistics.median(runs), runs, n, threads, kv.seq_len
 
 
+def _interleave_memory():
+    """set_mempolicy(MPOL_INTERLEAVE, all online nodes) for this (child) process: pages are spread round-robin over the
+    sockets instead of first-touch, and -- the point -- memory under an explicit policy is exempt from the kernel's
+    automatic NUMA balancing (no hinting faults / migrations while the young address space is sampled).  The in-process
+    placement keeps first-touch locality; the better of the two is reported.  Best effort: returns what happened."""
+    import ctypes
+    import platform
+    if platform.machine() != "x86_64":
+        return f"default (no syscall number for {platform.machine()})"
+    try:
+        ids = []
+        for part in open("/sys/devices/system/node/online").read().strip().split(","):
+            a, _, b = part.partition("-")
+            ids += list(range(int(a), int(b or a) + 1))
+        if len(ids) < 2 or max(ids) > 62:
+            return f"default ({len(ids)} NUMA node(s))"
+        mask = ctypes.c_ulong(sum(1 << i for i in ids))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(ctypes.c_long(238), ctypes.c_long(3), ctypes.byref(mask), ctypes.c_ulong(64))  # x86-64 set_mempolicy, MPOL_INTERLEAVE
+        return f"interleave over nodes {ids}" if rc == 0 else f"default (set_mempolicy errno {ctypes.get_errno()})"
+    except Exception as e:
+        return f"default ({type(e).__name__}: {e})"
+
+
 def _cpu_arm_child(argv):
     """`bench.py --cpu-arm-child <dir> <preset> <ctx> <budget_s> <repeats> <threads>`: the CPU arm in a process of its
     own.  The parent starts it with OMP_PROC_BIND / OMP_PLACES / OMP_NUM_THREADS already in the environment, and it
@@ -211,6 +235,7 @@ def _cpu_arm_child(argv):
     for the same loop in the main arm's process and in the test suite's."""
     import numpy as np
     from pegainfer_b200.config import PRESETS
+    print("CPU_ARM_MEMPOLICY " + _interleave_memory(), flush=True)
     d, preset, ctx, budget_s, repeats, threads = argv[0], argv[1], int(argv[2]), float(argv[3]), int(argv[4]), int(argv[5])
     names = json.load(open(os.path.join(d, "index.json")))
     w = {name: np.load(os.path.join(d, f"{i}.npy"), mmap_mode="r") for i, name in enumerate(names)}
@@ -239,12 +264,16 @@ def _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads):
         if r.returncode != 0 or not line:
             raise RuntimeError(f"cpu arm child failed (rc {r.returncode}): {r.stderr[-300:]}")
         d = json.loads(line[-1][len("CPU_ARM_RESULT "):])
+        pol = [ln[len("CPU_ARM_MEMPOLICY "):] for ln in r.stdout.splitlines() if ln.startswith("CPU_ARM_MEMPOLICY ")]
+        global _CHILD_MEMPOLICY
+        _CHILD_MEMPOLICY = pol[-1] if pol else "default"
         return d["rate"], d["runs"], d["n"], d["threads"], d["ctx_end"]
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
 _CPU_ARM_NOTE = ""
+_CHILD_MEMPOLICY = "default"
 
 
 def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
@@ -263,7 +292,8 @@ def cpu_decode_rate(cfg, weights_np, ctx, budget_s, repeats=3):
     threads = host_threads()
     results = []
     try:
-        results.append(("child process (numpy + oracle only)", _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads)))
+        res = _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads)
+        results.append((f"child process (numpy + oracle only, memory policy: {_CHILD_MEMPOLICY})", res))
     except Exception as e:
         print(f"[bench] cpu arm child unavailable ({type(e).__name__}: {e})", file=sys.stderr)
     try:
