@@ -247,7 +247,17 @@ def _cpu_decode_rate_child(cfg, weights_np, ctx, budget_s, repeats, threads):
     import shutil
     import tempfile
     import numpy as np
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    need = int(1.1 * sum(int(np.asarray(a).nbytes) for a in weights_np.values())) + (64 << 20)
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):  # the checkpoint travels as .npy files: RAM-backed if there is room
+        try:
+            if os.path.isdir(cand) and os.access(cand, os.W_OK) and shutil.disk_usage(cand).free > need:
+                base = cand
+                break
+        except OSError:
+            pass
+    if base is None:
+        raise RuntimeError(f"no scratch directory with {need >> 30} GiB free for the child's checkpoint copy")
     tmp = tempfile.mkdtemp(prefix="pk_cpu_arm_", dir=base)
     try:
         names = list(weights_np.keys())
