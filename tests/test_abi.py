@@ -65,7 +65,7 @@ def test_sass_is_blackwell_native(built):
 
 def test_prefill_gemm_plan_matches_the_measured_calibration():
     """pk_b200_gemm_plan (host arithmetic of gemm2.cu, no CUDA call) on a 148-SM GPU: the choices that were measured on B200
-    (profiles/README.md round 2, gpurun_out/c18_prefill_ops.log).  o_proj / down_proj at 2048 tokens must take the pair
+    (profiles/README.md round 2, profiles/r2_v3_prefill_ops.txt).  o_proj / down_proj at 2048 tokens must take the pair
     kernel's one-wave 320-wide tile (46 / 89 us; the single-CTA kernel needs 81 / 173 us) -- a cost-model slip that sent
     them back to the single-CTA kernel cost 1.4 ms of TTFT(2048) until it was calibrated."""
     from pegainfer_b200 import ffi
