@@ -28,7 +28,9 @@ Keys of the JSON line (see the task contract):
             CUDA-event time of the token's 145 GEMV launches, vs MEASURED_PEAKS.json hbm_gbs; `traffic` = measured
             dram bytes per launch from the committed ncu pass (profiles/gemv_traffic.json, per shape incl. lm_head)
   cpu_baseline  the CPU oracle (port of the reference forward) timed on the host cores at the GPU arm's context
-            length, OpenMP thread count set and reported, three repeats
+            length, OpenMP thread count set and reported; untimed steps until the step time is steady, then three
+            repeats; timed in two placements (a child process with numpy + the oracle only and interleaved memory, and
+            this process with first-touch memory), each bounded, the better one reported and both named in `sample`
 `--impl reference` times that CPU port alone (the reference has no CPU path of its own and its Rust
 host cannot be built here; oracle/_ref holds its CUDA kernels, which are GPU code: they are the `gpu_reference` leg).
 """
