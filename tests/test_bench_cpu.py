@@ -46,3 +46,17 @@ def test_reference_arm_prints_contract_line():
     assert "OpenMP" in line["cpu_baseline"]["sample"] and "ctx" in line["cpu_baseline"]["sample"]
     # both placements of the timed loop are tried (a child process without torch, and this process) and named
     assert "child process" in line["cpu_baseline"]["sample"] and "this process" in line["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm under torchrun like the GPU arm; rank 0 alone runs and prints the line,
+    the other ranks exit 0 without work (no process group is created)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_PROC_BIND", "OMP_PLACES")}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "4",
+                        "--warmup", "3", "--model", "qwen3-tiny"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"impl": "reference"' in ln]
+    assert len(lines) == 1, r.stdout[-1000:]
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
